@@ -1,0 +1,10 @@
+"""algebra_b200 — B200-native (sm_100a) backend for the arkworks-rs/algebra data-parallel hot path:
+variable-base MSM over short-Weierstrass G1 and the radix-2 NTT, behind the C ABI of include/algebra_b200.h.
+This package is only the host-side mirror of the reference interfaces; all arithmetic runs in
+libalgebra_b200.so (hand-written CUDA).  No CPU fallback."""
+from . import _lib, params                                    # noqa: F401
+from .domain import Radix2EvaluationDomain                    # noqa: F401
+from .msm import LengthMismatch, into_affine, msm, msm_unchecked, sum_points   # noqa: F401
+from .params import BLS12_381_G1, BN254_G1                    # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,109 @@
+// capi.cu — the extern "C" boundary declared in include/algebra_b200.h.
+#include <algorithm>
+#include "common.cuh"
+
+namespace ab200 {
+int ntt_dispatch(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset, cudaStream_t st);
+int ntt_clear_cache();
+int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st);
+int msm_set_window(int c);
+int msm_auto_window(size_t n, int scalar_bits);
+int msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds);
+int g1_sum_dispatch(int curve, const uint64_t *pts_host, size_t k, uint64_t *out_host, bool to_affine);
+int fp_op_dispatch(int field, int op, const void *a, const void *b, void *out, size_t n, int reps, cudaStream_t st);
+int ec_op_dispatch(int curve, int op, const void *a, const void *b, void *out, size_t n, cudaStream_t st);
+int gen_bases_dispatch(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, cudaStream_t st);
+int gen_scalars_dispatch(int field, uint64_t seed, size_t n, void *d_scalars, cudaStream_t st);
+}  // namespace ab200
+using namespace ab200;
+
+extern "C" {
+
+int b200_msm_sw_g1_dev(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz, void *stream) {
+    return msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, (cudaStream_t)stream);
+}
+
+int b200_msm_sw_g1(int curve, const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out_xyz) {
+    if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
+    if (!out_xyz || (n && (!bases || !scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
+    if (n == 0) return msm_dispatch(curve, nullptr, nullptr, 0, out_xyz, 0);
+    const size_t N = curve == B200_CURVE_BLS12_381 ? 6 : 4;
+    cudaStream_t st = 0;
+    void *d_bases = nullptr, *d_scalars = nullptr;
+    AB_CUDA(cudaMallocAsync(&d_bases, n * 2 * N * 8, st));
+    AB_CUDA(cudaMallocAsync(&d_scalars, n * 32, st));
+    AB_CUDA(cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    AB_CUDA(cudaMemcpyAsync(d_bases, bases, n * 2 * N * 8, cudaMemcpyHostToDevice, st));
+    int rc = msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, st);
+    cudaFreeAsync(d_bases, st);
+    cudaFreeAsync(d_scalars, st);
+    cudaStreamSynchronize(st);
+    return rc;
+}
+
+int b200_set_msm_window(int c) { return msm_set_window(c); }
+int b200_msm_window_for(int curve, size_t n) {
+    if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) return B200_EINVAL;
+    return msm_auto_window(n, curve == B200_CURVE_BLS12_381 ? 255 : 254);
+}
+int b200_g1_sum(int curve, const uint64_t *points_xyz, size_t k, uint64_t *out_xyz) { return g1_sum_dispatch(curve, points_xyz, k, out_xyz, false); }
+int b200_g1_into_affine(int curve, const uint64_t *xyz, uint64_t *out_xy) { return g1_sum_dispatch(curve, xyz, 1, out_xy, true); }
+
+int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset_offset, void *stream) {
+    int rc = ntt_dispatch(field, d_data, log_n, inverse, coset_offset, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const uint64_t *coset_offset) {
+    if (!data) { set_last_error("null data pointer"); return B200_EINVAL; }
+    if (field != B200_FIELD_BLS12_381_FR && field != B200_FIELD_BN254_FR) { set_last_error("unknown scalar field id"); return B200_EINVAL; }
+    if (log_n > (uint32_t)(field == B200_FIELD_BLS12_381_FR ? 32 : 28)) {
+        set_last_error("log_n exceeds TWO_ADICITY (Radix2EvaluationDomain::new would return None)");
+        return B200_ETOOLARGE;
+    }
+    const size_t bytes = ((size_t)32) << log_n;
+    cudaStream_t st = 0;
+    void *d = nullptr;
+    AB_CUDA(cudaMallocAsync(&d, bytes, st));
+    AB_CUDA(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, st));
+    int rc = ntt_dispatch(field, d, log_n, inverse, coset_offset, st);
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H", __FILE__, __LINE__);
+    }
+    cudaFreeAsync(d, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    return rc;
+}
+int b200_clear_cache(void) { return ntt_clear_cache(); }
+
+int b200_gen_bases_dev(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, void *stream) {
+    int rc = gen_bases_dispatch(curve, seed, n, d_bases, d_b, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int b200_gen_scalars_dev(int field, uint64_t seed, size_t n, void *d_scalars, void *stream) {
+    int rc = gen_scalars_dispatch(field, seed, n, d_scalars, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int b200_fp_op_dev(int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n, int reps, void *stream) {
+    int rc = fp_op_dispatch(field, op, d_a, d_b, d_out, n, reps, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int b200_ec_op_dev(int curve, int op, const void *d_a, const void *d_b, void *d_out, size_t n, void *stream) {
+    int rc = ec_op_dispatch(curve, op, d_a, d_b, d_out, n, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int b200_msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds) { return msm_last_timings(ms7, c, windows, bucket_adds); }
+
+}  // extern "C"

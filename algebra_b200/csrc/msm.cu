@@ -1,0 +1,538 @@
+// msm.cu — variable-base MSM over short-Weierstrass G1 (a = 0) for sm_100a: bucket method (Pippenger) with
+// signed c-bit digits, counting-sort bucket assignment and thread-per-bucket XYZZ accumulation.
+//
+// Replaces VariableBaseMSM::msm_unchecked for Projective<P> (ec/src/scalar_mul/variable_base/mod.rs:59-64
+// -> msm_bigint_wnaf_parallel :437-503).  Same mathematics, GPU schedule:
+//   reference (per window, serial over points)          here (all windows at once)
+//   into_bigint + make_digits (:60-62, :754-794)    ->  msm_digits_kernel<HIST>: REDC + signed digits, histogram of
+//                                                       (window, |digit|) with global atomics
+//   buckets[|d|-1] +=/-= base  (:467-475)           ->  exclusive scan of the histogram, msm_digits_kernel<SCATTER>
+//                                                       writes (index | sign) into bucket-sorted order, then
+//                                                       msm_accumulate_kernel: one thread per (window, bucket) runs the
+//                                                       reference's `Bucket += Affine` (bucket.rs:168-238) over its run
+//   running-sum  res += running_sum (:478-484)      ->  msm_bucket_reduce_kernel: each thread does the running sum over a
+//                                                       chunk of m buckets plus (chunk offset) * (chunk total);
+//                                                       msm_sum_partials_kernel tree-adds the chunks of a window
+//   window combine, c doublings per window (:489-502) -> msm_window_combine_kernel (Jacobian, one thread)
+// EC addition is commutative/associative, so bucket order, atomics and chunking do not change the group element;
+// results are compared with the reference after into_affine(), limb-exact.
+// The digit recoding is the reference's make_digits (top window unsigned), so bucket counts per window are
+// 2^(c-1), and 2^(lambda-(W-1)c) for the top window.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace ab200 {
+
+struct CurveBls {
+    using Fq = BlsFq;
+    using Fr = BlsFr;
+    static constexpr int SCALAR_BITS = 255;  // Fr::MODULUS_BIT_SIZE (variable_base/mod.rs:451)
+};
+struct CurveBn {
+    using Fq = BnFq;
+    using Fr = BnFr;
+    static constexpr int SCALAR_BITS = 254;
+};
+
+struct MsmGeom {
+    int c, W, top_bits;          // window bits, number of windows, bits in the top window
+    uint32_t nb;                 // buckets per non-top window = 2^(c-1)
+    uint32_t nb_top;             // buckets in the top window   = 2^top_bits
+    uint32_t total_buckets;      // (W-1)*nb + nb_top
+};
+
+static MsmGeom make_geom(int c, int scalar_bits) {
+    MsmGeom g;
+    g.c = c;
+    g.W = (scalar_bits + c - 1) / c;  // digits_count (:452)
+    g.top_bits = scalar_bits - (g.W - 1) * c;
+    g.nb = 1u << (c - 1);
+    g.nb_top = 1u << g.top_bits;
+    g.total_buckets = (uint32_t)(g.W - 1) * g.nb + g.nb_top;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// digits: canonical scalar -> signed digits (make_digits, :754-794); MODE 0 = histogram, 1 = scatter
+// ------------------------------------------------------------------------------------------------
+template <class C, int MODE>
+__global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restrict__ scalars, size_t n, MsmGeom g,
+                                                         uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
+    using FR = Fp<typename C::Fr>;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8], k[10];
+    load_limbs_nc<8>(s, scalars + i * 8);
+    FR::from_mont(k, s);  // into_bigint (:60-62)
+    k[8] = 0;
+    k[9] = 0;
+    const int c = g.c;
+    const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < g.W; w++) {
+        const int bit = w * c, wi = bit >> 5, sh = bit & 31;
+        uint64_t two = ((uint64_t)k[wi + 1] << 32) | k[wi];
+        uint32_t coef = ((uint32_t)(two >> sh) & mask) + carry;
+        uint32_t mag, neg = 0;
+        if (w == g.W - 1) {  // top digit stays unsigned (:789-791)
+            mag = coef;
+        } else {
+            carry = (coef + half) >> c;
+            if (carry) { mag = (1u << c) - coef; neg = 1; }  // digit = coef - 2^c in [-2^(c-1), 0)
+            else mag = coef;
+        }
+        if (mag) {
+            uint32_t gid = (uint32_t)w * g.nb + (mag - 1);
+            if (MODE == 0) {
+                atomicAdd(&counts_or_cursor[gid], 1u);
+            } else {
+                uint32_t pos = atomicAdd(&counts_or_cursor[gid], 1u);
+                sorted[pos] = (uint32_t)i | (neg << 31);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of u32 counts (total < 2^32): block totals -> serial scan of totals -> apply
+// ------------------------------------------------------------------------------------------------
+static constexpr int kScanThreads = 512, kScanPerThread = 8, kScanBlock = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += y;
+        }
+        warp_sums[lane] = ws;  // inclusive
+    }
+    __syncthreads();
+    uint32_t before = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[(blockDim.x >> 5) - 1];
+    return before + x - v;  // exclusive
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_block_totals_kernel(const uint32_t *in, size_t n, uint32_t *block_totals) {
+    size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; k++)
+        if (base + k < n) s += in[base + k];
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_totals[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_totals_kernel(uint32_t *block_totals, size_t nblocks) {
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (size_t base = 0; base < nblocks; base += kScanThreads) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < nblocks ? block_totals[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        uint32_t r0 = running;
+        if (i < nblocks) block_totals[i] = r0 + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) running = r0 + total;
+        __syncthreads();
+    }
+}
+// out[i] = exclusive prefix; out[n] = grand total (out has n+1 entries)
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t *in, size_t n, const uint32_t *block_offsets, uint32_t *out) {
+    size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    uint32_t v[kScanPerThread], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total) + block_offsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanPerThread; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+        if (base + k == n - 1) out[n] = ex;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucket accumulation: one thread per (window, bucket); the hot loop (Bucket += Affine, bucket.rs:168-238)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                             const uint32_t *__restrict__ offsets, uint32_t total_buckets,
+                                                             uint32_t *__restrict__ buckets) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total_buckets) return;
+    uint32_t k = offsets[gid];
+    const uint32_t end = offsets[gid + 1];
+    typename E::B acc;
+    E::xyzz_set_zero(acc);
+    uint32_t cx[L], cy[L], nx[L], ny[L];
+    uint32_t e = 0, e_next = 0;
+    if (k < end) {
+        e = __ldg(sorted + k);
+        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
+        load_limbs_nc<L>(cx, bp);
+        load_limbs_nc<L>(cy, bp + L);
+    }
+    while (k < end) {
+        const bool more = (k + 1 < end);
+        if (more) {  // issue the next gather before the ~10 modmuls of this addition
+            e_next = __ldg(sorted + k + 1);
+            const uint32_t *bp = bases + (size_t)(e_next & 0x7fffffffu) * (2 * L);
+            load_limbs_nc<L>(nx, bp);
+            load_limbs_nc<L>(ny, bp + L);
+        }
+        E::madd(acc, cx, cy, (e >> 31) != 0);
+        if (more) {
+            limbs_copy<L>(cx, nx);
+            limbs_copy<L>(cy, ny);
+            e = e_next;
+        }
+        k++;
+    }
+    uint32_t *o = buckets + (size_t)gid * (4 * L);
+    store_limbs<L>(o, acc.x);
+    store_limbs<L>(o + L, acc.y);
+    store_limbs<L>(o + 2 * L, acc.zz);
+    store_limbs<L>(o + 3 * L, acc.zzz);
+}
+
+template <class P> __device__ __forceinline__ void load_xyzz(Xyzz<P> &b, const uint32_t *p) {
+    constexpr int L = P::L;
+    load_limbs<L>(b.x, p);
+    load_limbs<L>(b.y, p + L);
+    load_limbs<L>(b.zz, p + 2 * L);
+    load_limbs<L>(b.zzz, p + 3 * L);
+}
+template <class P> __device__ __forceinline__ void store_xyzz(uint32_t *p, const Xyzz<P> &b) {
+    constexpr int L = P::L;
+    store_limbs<L>(p, b.x);
+    store_limbs<L>(p + L, b.y);
+    store_limbs<L>(p + 2 * L, b.zz);
+    store_limbs<L>(p + 3 * L, b.zzz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucket reduction.  Window w needs S_w = sum_j (j+1) * B_w[j]  (:478-484).  Thread t of a window takes buckets
+// [t*m, (t+1)*m): running sum gives  sum_l (l+1)*B[t*m+l]  and the chunk total R_t; adding (t*m) * R_t (double-and-add)
+// makes its contribution complete.  partial index = window * chunks_stride + t.
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const uint32_t *__restrict__ buckets, MsmGeom g, int log_m,
+                                                                uint32_t chunks_per_window, uint32_t *__restrict__ partials) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t w = tid / chunks_per_window, t = tid % chunks_per_window;
+    if (w >= (uint32_t)g.W) return;
+    const uint32_t nbw = (w == (uint32_t)g.W - 1) ? g.nb_top : g.nb;
+    const uint32_t m = 1u << log_m;
+    typename E::B run, sum;
+    E::xyzz_set_zero(run);
+    E::xyzz_set_zero(sum);
+    const uint32_t lo = t * m;
+    if (lo < nbw) {
+        const uint32_t hi = min(lo + m, nbw);
+        const uint32_t *base = buckets + ((size_t)w * g.nb) * (4 * L);
+        for (uint32_t j = hi; j-- > lo;) {
+            typename E::B b;
+            load_xyzz<P>(b, base + (size_t)j * (4 * L));
+            E::xyzz_add(run, b);
+            E::xyzz_add(sum, run);
+        }
+        // sum += lo * run
+        if (lo != 0 && !E::xyzz_is_zero(run)) {
+            typename E::B acc;
+            E::xyzz_set_zero(acc);
+            for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+                if (!E::xyzz_is_zero(acc)) E::xyzz_dbl(acc);
+                if ((lo >> bit) & 1) E::xyzz_add(acc, run);
+            }
+            E::xyzz_add(sum, acc);
+        }
+    }
+    store_xyzz<P>(partials + ((size_t)w * chunks_per_window + t) * (4 * L), sum);
+}
+
+// one block per window: strided sums then a shared-memory tree; result -> window_sums[w]
+template <class C>
+__global__ void __launch_bounds__(128) msm_sum_partials_kernel(const uint32_t *__restrict__ partials, uint32_t chunks_per_window,
+                                                               uint32_t *__restrict__ window_sums) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    extern __shared__ uint32_t sm[];
+    const uint32_t w = blockIdx.x;
+    typename E::B acc;
+    E::xyzz_set_zero(acc);
+    for (uint32_t t = threadIdx.x; t < chunks_per_window; t += blockDim.x) {
+        typename E::B b;
+        load_xyzz<P>(b, partials + ((size_t)w * chunks_per_window + t) * (4 * L));
+        E::xyzz_add(acc, b);
+    }
+    store_xyzz<P>(sm + threadIdx.x * (4 * L), acc);
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            typename E::B a, b;
+            load_xyzz<P>(a, sm + threadIdx.x * (4 * L));
+            load_xyzz<P>(b, sm + (threadIdx.x + s) * (4 * L));
+            E::xyzz_add(a, b);
+            store_xyzz<P>(sm + threadIdx.x * (4 * L), a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        typename E::B a;
+        load_xyzz<P>(a, sm);
+        store_xyzz<P>(window_sums + (size_t)w * (4 * L), a);
+    }
+}
+
+// total = sum_w 2^(c*w) * S_w by Horner (:489-502); Jacobian result (x, y, z) -> out (3L words)
+template <class C> __global__ void msm_window_combine_kernel(const uint32_t *__restrict__ window_sums, int W, int c, uint32_t *__restrict__ out) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    typename E::J total;
+    E::jac_set_zero(total);
+    for (int w = W - 1; w >= 0; w--) {
+        typename E::B b;
+        typename E::J j;
+        load_xyzz<P>(b, window_sums + (size_t)w * (4 * L));
+        E::xyzz_to_jac(j, b);
+        E::jac_add(total, j);  // Projective += &Bucket (bucket.rs:345-359)
+        if (w > 0)
+            for (int d = 0; d < c; d++) E::jac_dbl(total);
+    }
+    store_limbs<L>(out, total.x);
+    store_limbs<L>(out + L, total.y);
+    store_limbs<L>(out + 2 * L, total.z);
+}
+
+// sum of k Jacobian points (multi-GPU gather reduce), one thread
+template <class C> __global__ void jac_sum_kernel(const uint32_t *__restrict__ pts, size_t k, uint32_t *__restrict__ out) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    typename E::J total;
+    E::jac_set_zero(total);
+    for (size_t i = 0; i < k; i++) {
+        typename E::J j;
+        load_limbs<L>(j.x, pts + i * 3 * L);
+        load_limbs<L>(j.y, pts + i * 3 * L + L);
+        load_limbs<L>(j.z, pts + i * 3 * L + 2 * L);
+        E::jac_add(total, j);
+    }
+    if (E::jac_is_zero(total)) E::jac_set_zero(total);
+    store_limbs<L>(out, total.x);
+    store_limbs<L>(out + L, total.y);
+    store_limbs<L>(out + 2 * L, total.z);
+}
+template <class C> __global__ void jac_to_affine_kernel(const uint32_t *__restrict__ pts, size_t k, uint32_t *__restrict__ out) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    typename E::J j;
+    load_limbs<L>(j.x, pts + i * 3 * L);
+    load_limbs<L>(j.y, pts + i * 3 * L + L);
+    load_limbs<L>(j.z, pts + i * 3 * L + 2 * L);
+    uint32_t ax[L], ay[L];
+    E::jac_to_affine(ax, ay, j);
+    store_limbs<L>(out + i * 2 * L, ax);
+    store_limbs<L>(out + i * 2 * L + L, ay);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------
+static thread_local int t_window_override = 0;
+struct MsmTimings {
+    float ms[7] = {0, 0, 0, 0, 0, 0, 0};
+    int c = 0, W = 0;
+    unsigned long long bucket_adds = 0;
+};
+static thread_local MsmTimings t_last;
+
+int msm_set_window(int c) {
+    if (c < 0 || c > 24) { set_last_error("window size must be in [1,24] (0 = automatic)"); return B200_EINVAL; }
+    t_window_override = c;
+    return 0;
+}
+
+// Cost model (Fq modmuls): accumulation 10 per (point, window) inflated by the expected slowest-lane excess of a warp
+// of Poisson(lambda) bucket loads, reduction ~30 per bucket (two XYZZ adds + scalar-multiple overhead).
+int msm_auto_window(size_t n, int scalar_bits) {
+    if (n < 32) return 3;  // same floor as the reference (:445-449)
+    double best = 1e300;
+    int best_c = 3;
+    for (int c = 4; c <= 22; c++) {
+        MsmGeom g = make_geom(c, scalar_bits);
+        if ((double)g.total_buckets * 192.0 > 24e9) continue;
+        double lambda = (double)n / (double)g.nb;
+        double imbalance = 1.0 + 2.2 / std::sqrt(lambda + 1.0);
+        double acc = 10.0 * (double)n * g.W * imbalance;
+        double red = 30.0 * (double)g.total_buckets;
+        // very small buckets-per-window counts starve the GPU: need ~150k threads to fill 148 SMs
+        double par = (double)g.total_buckets < 150000.0 ? 150000.0 / (double)g.total_buckets : 1.0;
+        double cost = acc * std::min(par, 8.0) + red;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d_scalars, size_t n, uint32_t *d_out, cudaStream_t st) {
+    constexpr int L = C::Fq::L;
+    if (n >= ((size_t)1 << 31)) { set_last_error("n must be < 2^31"); return B200_ETOOLARGE; }
+    const int c = t_window_override ? t_window_override : msm_auto_window(n, C::SCALAR_BITS);
+    const MsmGeom g = make_geom(c, C::SCALAR_BITS);
+    const size_t nb_total = g.total_buckets;
+    const size_t max_entries = n * (size_t)g.W;
+    if (max_entries >= ((size_t)1 << 32)) { set_last_error("n * windows must be < 2^32"); return B200_ETOOLARGE; }
+
+    cudaEvent_t ev[7];
+    for (auto &e : ev) AB_CUDA(cudaEventCreate(&e));
+    uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *sorted = nullptr, *block_totals = nullptr;
+    uint32_t *buckets = nullptr, *partials = nullptr, *window_sums = nullptr;
+    const size_t scan_blocks = (nb_total + kScanBlock - 1) / kScanBlock;
+    AB_CUDA(cudaMallocAsync(&counts, nb_total * 4, st));
+    AB_CUDA(cudaMallocAsync(&offsets, (nb_total + 1) * 4, st));
+    AB_CUDA(cudaMallocAsync(&cursor, nb_total * 4, st));
+    AB_CUDA(cudaMallocAsync(&sorted, std::max<size_t>(max_entries, 1) * 4, st));
+    AB_CUDA(cudaMallocAsync(&block_totals, scan_blocks * 4, st));
+    AB_CUDA(cudaMallocAsync(&buckets, nb_total * 4 * L * 4, st));
+    // reduction geometry: chunk of m = 2^log_m buckets per thread
+    int log_m = 5;
+    while (log_m > 0 && (g.nb >> log_m) < 64) log_m--;
+    const uint32_t max_nb = std::max(g.nb, g.nb_top);
+    const uint32_t chunks = (max_nb + (1u << log_m) - 1) >> log_m;
+    AB_CUDA(cudaMallocAsync(&partials, (size_t)g.W * chunks * 4 * L * 4, st));
+    AB_CUDA(cudaMallocAsync(&window_sums, (size_t)g.W * 4 * L * 4, st));
+
+    AB_CUDA(cudaEventRecord(ev[0], st));
+    AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
+    const unsigned dblocks = (unsigned)((n + 255) / 256);
+    msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(d_scalars, n, g, counts, nullptr);
+    AB_LAUNCHED();
+    AB_CUDA(cudaEventRecord(ev[1], st));
+    scan_block_totals_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals);
+    AB_LAUNCHED();
+    scan_totals_kernel<<<1, kScanThreads, 0, st>>>(block_totals, scan_blocks);
+    AB_LAUNCHED();
+    scan_apply_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals, offsets);
+    AB_LAUNCHED();
+    AB_CUDA(cudaMemcpyAsync(cursor, offsets, nb_total * 4, cudaMemcpyDeviceToDevice, st));
+    AB_CUDA(cudaEventRecord(ev[2], st));
+    msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(d_scalars, n, g, cursor, sorted);
+    AB_LAUNCHED();
+    AB_CUDA(cudaEventRecord(ev[3], st));
+    msm_accumulate_kernel<C><<<(unsigned)((nb_total + 127) / 128), 128, 0, st>>>(d_bases, sorted, offsets, (uint32_t)nb_total, buckets);
+    AB_LAUNCHED();
+    AB_CUDA(cudaEventRecord(ev[4], st));
+    const unsigned rthreads = (unsigned)g.W * chunks;
+    msm_bucket_reduce_kernel<C><<<(rthreads + 127) / 128, 128, 0, st>>>(buckets, g, log_m, chunks, partials);
+    AB_LAUNCHED();
+    msm_sum_partials_kernel<C><<<g.W, 128, 128 * 4 * L * 4, st>>>(partials, chunks, window_sums);
+    AB_LAUNCHED();
+    AB_CUDA(cudaEventRecord(ev[5], st));
+    msm_window_combine_kernel<C><<<1, 32, 0, st>>>(window_sums, g.W, g.c, d_out);
+    AB_LAUNCHED();
+    AB_CUDA(cudaEventRecord(ev[6], st));
+
+    uint32_t total_entries = 0;
+    AB_CUDA(cudaMemcpyAsync(&total_entries, offsets + nb_total, 4, cudaMemcpyDeviceToHost, st));
+    for (uint32_t *p : {counts, offsets, cursor, sorted, block_totals, buckets, partials, window_sums}) AB_CUDA(cudaFreeAsync(p, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 6; i++) AB_CUDA(cudaEventElapsedTime(&t_last.ms[i], ev[i], ev[i + 1]));
+    AB_CUDA(cudaEventElapsedTime(&t_last.ms[6], ev[0], ev[6]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    t_last.c = g.c;
+    t_last.W = g.W;
+    t_last.bucket_adds = total_entries;
+    return 0;
+}
+
+int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st) {
+    if (!out_xyz_host || (n && (!d_bases || !d_scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
+    if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
+    const int L = curve == B200_CURVE_BLS12_381 ? 12 : 8;
+    if (n == 0) {  // Projective::zero() = (1,1,0) (group.rs:142-158)
+        for (int i = 0; i < 3 * L / 2; i++) out_xyz_host[i] = 0;
+        for (int i = 0; i < L; i++) {
+            uint32_t one = curve == B200_CURVE_BLS12_381 ? BlsFq::ONE(i) : BnFq::ONE(i);
+            for (int k = 0; k < 2; k++) out_xyz_host[(k * L + i) / 2] |= (uint64_t)one << (32 * ((k * L + i) & 1));
+        }
+        return 0;
+    }
+    uint32_t *d_out = nullptr;
+    AB_CUDA(cudaMallocAsync(&d_out, 3 * L * 4, st));
+    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st)
+                                           : msm_run<CurveBn>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st);
+    if (rc) return rc;
+    AB_CUDA(cudaMemcpyAsync(out_xyz_host, d_out, 3 * L * 4, cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaFreeAsync(d_out, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds) {
+    if (ms7) for (int i = 0; i < 7; i++) ms7[i] = t_last.ms[i];
+    if (c) *c = t_last.c;
+    if (windows) *windows = t_last.W;
+    if (bucket_adds) *bucket_adds = t_last.bucket_adds;
+    return 0;
+}
+
+int g1_sum_dispatch(int curve, const uint64_t *pts_host, size_t k, uint64_t *out_host, bool to_affine) {
+    if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
+    if (!pts_host || !out_host) { set_last_error("null pointer"); return B200_EINVAL; }
+    const int L = curve == B200_CURVE_BLS12_381 ? 12 : 8;
+    const size_t in_words = k * 3 * L, out_words = to_affine ? k * 2 * L : 3 * L;
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t st = 0;
+    AB_CUDA(cudaMallocAsync(&d_in, std::max<size_t>(in_words, 1) * 4, st));
+    AB_CUDA(cudaMallocAsync(&d_out, std::max<size_t>(out_words, 1) * 4, st));
+    AB_CUDA(cudaMemcpyAsync(d_in, pts_host, in_words * 4, cudaMemcpyHostToDevice, st));
+    if (to_affine) {
+        if (curve == B200_CURVE_BLS12_381) jac_to_affine_kernel<CurveBls><<<(unsigned)((k + 31) / 32), 32, 0, st>>>(d_in, k, d_out);
+        else jac_to_affine_kernel<CurveBn><<<(unsigned)((k + 31) / 32), 32, 0, st>>>(d_in, k, d_out);
+    } else {
+        if (curve == B200_CURVE_BLS12_381) jac_sum_kernel<CurveBls><<<1, 32, 0, st>>>(d_in, k, d_out);
+        else jac_sum_kernel<CurveBn><<<1, 32, 0, st>>>(d_in, k, d_out);
+    }
+    AB_LAUNCHED();
+    AB_CUDA(cudaMemcpyAsync(out_host, d_out, out_words * 4, cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaFreeAsync(d_in, st));
+    AB_CUDA(cudaFreeAsync(d_out, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace ab200

@@ -1,0 +1,105 @@
+"""Host-side mirror of `ark_ec::VariableBaseMSM` for short-Weierstrass G1 (ec/src/scalar_mul/variable_base/mod.rs:37-151)
+over the C ABI.  Same names, argument meaning and error behaviour as the reference:
+
+  msm(bases, scalars)            -> Jacobian limbs, or raises LengthMismatch(min_len) like `Err(min_len)` (:73-77)
+  msm_unchecked(bases, scalars)  -> silently truncates to the shorter input (:59-64)
+
+bases:   (n, 2N) uint64 Montgomery affine points, numpy (host) or torch CUDA tensor (device-resident, dtype int64/uint64)
+scalars: (n, 4)  uint64 Montgomery Fr elements, same container kind as `bases`
+result:  numpy (3N,) uint64 = Projective (x, y, z), Montgomery limbs; `into_affine` gives the comparison form."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .params import CURVES, G1Curve
+
+
+class LengthMismatch(ValueError):
+    """`Err(min_len)` of VariableBaseMSM::msm"""
+
+    def __init__(self, min_len: int):
+        super().__init__(f"bases and scalars differ in length; min_len = {min_len}")
+        self.min_len = min_len
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _rows(x, width: int) -> int:
+    if _is_torch(x):
+        return x.numel() // width
+    return np.asarray(x).size // width
+
+
+def msm_unchecked(curve: G1Curve | int, bases, scalars) -> np.ndarray:
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    N = cv.N
+    n = min(_rows(bases, 2 * N), _rows(scalars, 4))
+    out = np.zeros(3 * N, dtype=np.uint64)
+    outp = out.ctypes.data_as(ctypes.c_void_p)
+    if _is_torch(bases) != _is_torch(scalars):
+        raise TypeError("bases and scalars must both be numpy arrays or both be torch CUDA tensors")
+    if _is_torch(bases):
+        import torch
+        if not (bases.is_cuda and scalars.is_cuda and bases.is_contiguous() and scalars.is_contiguous()):
+            raise TypeError("device path needs contiguous CUDA tensors")
+        assert bases.element_size() == 8 and scalars.element_size() == 8
+        with torch.cuda.device(bases.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().b200_msm_sw_g1_dev(cv.cid, bases.data_ptr(), scalars.data_ptr(), n, outp, st))
+    else:
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * N)[:n]
+        s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)[:n]
+        b, s = np.ascontiguousarray(b), np.ascontiguousarray(s)
+        _lib.check(_lib.lib().b200_msm_sw_g1(cv.cid, b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), n, outp))
+    return out
+
+
+def msm(curve: G1Curve | int, bases, scalars) -> np.ndarray:
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    nb, ns = _rows(bases, 2 * cv.N), _rows(scalars, 4)
+    if nb != ns:
+        raise LengthMismatch(min(nb, ns))
+    return msm_unchecked(cv, bases, scalars)
+
+
+def into_affine(curve: G1Curve | int, xyz: np.ndarray) -> np.ndarray:
+    """Projective -> Affine (ec/src/models/short_weierstrass/affine.rs:374-396); identity -> (0,0)."""
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    xyz = np.ascontiguousarray(xyz, dtype=np.uint64).reshape(3 * cv.N)
+    out = np.zeros(2 * cv.N, dtype=np.uint64)
+    _lib.check(_lib.lib().b200_g1_into_affine(cv.cid, xyz.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def sum_points(curve: G1Curve | int, points_xyz: np.ndarray) -> np.ndarray:
+    """sum of k Projective points ((k, 3N) uint64) — `Sum for Projective`, used after the multi-GPU gather."""
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    pts = np.ascontiguousarray(points_xyz, dtype=np.uint64).reshape(-1, 3 * cv.N)
+    out = np.zeros(3 * cv.N, dtype=np.uint64)
+    _lib.check(_lib.lib().b200_g1_sum(cv.cid, pts.ctypes.data_as(ctypes.c_void_p), pts.shape[0], out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def set_window(c: int) -> None:
+    """Pippenger window override (0 = automatic) — for the window sweep of BASELINE configs[1]."""
+    _lib.check(_lib.lib().b200_set_msm_window(c))
+
+
+def window_for(curve: G1Curve | int, n: int) -> int:
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    return _lib.lib().b200_msm_window_for(cv.cid, n)
+
+
+def last_timings() -> dict:
+    ms = (ctypes.c_float * 7)()
+    c, w, adds = ctypes.c_int(), ctypes.c_int(), ctypes.c_ulonglong()
+    _lib.lib().b200_msm_last_timings(ms, ctypes.byref(c), ctypes.byref(w), ctypes.byref(adds))
+    names = ["digits_hist", "scan", "scatter", "accumulate", "reduce", "combine", "total"]
+    d = {k: float(v) for k, v in zip(names, ms)}
+    d.update(c=c.value, windows=w.value, bucket_adds=adds.value)
+    return d

@@ -1,0 +1,124 @@
+/*
+ * algebra_b200.h — C ABI of the B200-native backend for the arkworks-rs/algebra hot path
+ * (variable-base MSM over short-Weierstrass G1, radix-2 NTT over the scalar field).
+ *
+ * This is the boundary a Rust backend crate binds with `extern "C"`.  Plain
+ * pointers and sizes only; no torch / CUDA types in any signature (streams travel as void*).
+ *
+ * Data layout = arkworks' in-memory layout (NOT ark-serialize bytes):
+ *   Fp<MontBackend<_,N>,N>  = N little-endian u64 limbs, Montgomery form (R = 2^(64N)), value < p
+ *                             (ff/src/fields/models/fp/mod.rs:107-115, ff/src/biginteger/mod.rs:34)
+ *   Affine<P>               = x limbs, then y limbs; the identity is (0,0) when ZeroFlag = ()
+ *                             (ec/src/models/short_weierstrass/affine.rs:30-37,91-104)
+ *   Projective<P>           = x, y, z limbs (Jacobian); z == 0 is the identity and is returned as
+ *                             (R, R, 0) like `Projective::zero()` (group.rs:142-158)
+ * N = 6 for BLS12-381 Fq, 4 for BLS12-381 Fr / BN254 Fq / BN254 Fr.
+ *
+ * Every function returns 0 on success, a negative B200_E* code on argument errors and a positive
+ * cudaError_t value on CUDA failures; b200_last_error() gives the message.  All entry points are
+ * thread-safe (per-device context behind a mutex).  There is no CPU fallback: without a CUDA device
+ * every compute entry point fails with a CUDA error.
+ */
+#ifndef ALGEBRA_B200_H
+#define ALGEBRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* curve ids (G1 only)            reference parameters                                         */
+#define B200_CURVE_BLS12_381 0 /* curves/bls12_381/src/curves/g1.rs:28-95                      */
+#define B200_CURVE_BN254 1     /* curves/bn254/src/curves/g1.rs:16-90                          */
+/* scalar-field ids for the NTT */
+#define B200_FIELD_BLS12_381_FR 0 /* curves/bls12_381/src/fields/fr.rs, TWO_ADICITY = 32        */
+#define B200_FIELD_BN254_FR 1     /* curves/bn254/src/fields/fr.rs,     TWO_ADICITY = 28        */
+
+#define B200_EINVAL (-1)      /* bad id / null pointer                                          */
+#define B200_ETOOLARGE (-2)   /* log_n > TWO_ADICITY: Radix2EvaluationDomain::new returns None  */
+#define B200_ENOMEM (-3)
+
+const char *b200_version(void);
+const char *b200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * MSM — replaces the body of `SWCurveConfig::msm` (ec/src/models/short_weierstrass/mod.rs:111-119),
+ * i.e. `VariableBaseMSM::msm_unchecked` (ec/src/scalar_mul/variable_base/mod.rs:59-64) for
+ * Projective<P>: sum_i scalars[i] * bases[i] over the first n pairs.  The caller does the
+ * `bases.len() == scalars.len()` check and maps a mismatch to Err(min_len) (:73-77).
+ *   bases   n x 2N u64  (affine, Montgomery)        scalars  n x 4 u64 (Fr, Montgomery)
+ *   out_xyz 3N u64      (Jacobian, Montgomery)
+ * The result is the same group element the reference computes (limb-identical after into_affine()).
+ * --------------------------------------------------------------------------------------------- */
+int b200_msm_sw_g1(int curve, const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out_xyz);
+
+/* Same, operands already resident in device memory of the current device (bases can be uploaded once
+ * and reused, the analogue of holding `&[G1Affine]` across calls); out_xyz is a HOST pointer.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Synchronises before returning. */
+int b200_msm_sw_g1_dev(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz,
+                       void *stream);
+
+/* Pippenger window size c used by subsequent MSM calls on this thread's device: 0 = automatic.
+ * (The reference's rule is ln_without_floats(n)+2, ec/src/scalar_mul/variable_base/mod.rs:445-449; any c
+ * yields the same group element.)  b200_msm_window_for(n) reports what "automatic" picks. */
+int b200_set_msm_window(int c);
+int b200_msm_window_for(int curve, size_t n);
+
+/* sum of k Jacobian points (k x 3N u64, host) -> out_xyz: the local "reduce" after the multi-GPU
+ * all-gather of per-rank partial sums (Projective::add_assign, group.rs:450-538). */
+int b200_g1_sum(int curve, const uint64_t *points_xyz, size_t k, uint64_t *out_xyz);
+/* Jacobian -> affine (affine.rs:374-396): 3N u64 in, 2N u64 out; identity -> (0,0). */
+int b200_g1_into_affine(int curve, const uint64_t *xyz, uint64_t *out_xy);
+
+/* ---------------------------------------------------------------------------------------------
+ * NTT — replaces Radix2EvaluationDomain::{fft_in_place, ifft_in_place} after their resize step
+ * (poly/src/domain/radix2/mod.rs:140-153; fft.rs:74-88): natural order in, natural order out,
+ *   forward: out[i] = sum_j in[j] * (h * g^i)^j          inverse: the exact inverse incl. 1/n,
+ * g = get_root_of_unity(2^log_n) (ff/src/fields/fft_friendly.rs:66-82), h = coset offset.
+ *   data          2^log_n x 4 u64 (Montgomery Fr), transformed in place
+ *   coset_offset  NULL (h = 1) or 4 u64 Montgomery limbs of h (domain.coset_offset())
+ * Returns B200_ETOOLARGE when log_n > TWO_ADICITY (where Radix2EvaluationDomain::new gives None).
+ * --------------------------------------------------------------------------------------------- */
+int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const uint64_t *coset_offset);
+/* device-resident variant: d_data is a device pointer; coset_offset stays a host pointer. */
+int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset_offset,
+                    void *stream);
+/* drop cached twiddle tables / scratch of the current device */
+int b200_clear_cache(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic-input generators for benchmarks and large-size property tests (device-resident).
+ *   b200_gen_bases_dev:   P_i = b_i * G for a splitmix64 stream b_i (seeded), written as affine
+ *                         Montgomery points to d_bases (n x 2N u64) and b_i to d_b (n u64, may be
+ *                         NULL) — so the exact MSM answer is (sum s_i*b_i mod r) * G.
+ *   b200_gen_scalars_dev: n uniform Fr elements (rejection sampling like Fp::rand,
+ *                         ff/src/fields/models/fp/mod.rs:521-548), interpreted as Montgomery limbs.
+ * --------------------------------------------------------------------------------------------- */
+int b200_gen_bases_dev(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, void *stream);
+int b200_gen_scalars_dev(int field, uint64_t seed, size_t n, void *d_scalars, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Element-wise primitive kernels (parity tests and the field micro-benchmark, cf.
+ * bench-templates/src/macros/field.rs:69-155).  Device pointers; 1 thread per element.
+ *   b200_fp_op_dev  field: 0 BLS Fq, 1 BLS Fr, 2 BN254 Fq, 3 BN254 Fr
+ *                   op: 0 mul 1 add 2 sub 3 square 4 double 5 neg 6 into_bigint 7 from_bigint 8 inverse
+ *   b200_ec_op_dev  op: 0 bucket+=affine 1 bucket-=affine 2 bucket+=bucket 3 bucket.double
+ *                       4 bucket->jacobian 5 jacobian->affine 6 jacobian+=jacobian 7 jacobian.double
+ *                   (bucket = XYZZ, 4N u64; jacobian 3N; affine 2N)
+ *   reps > 1 re-applies the op to its own output (micro-benchmark mode).
+ * --------------------------------------------------------------------------------------------- */
+int b200_fp_op_dev(int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n, int reps, void *stream);
+int b200_ec_op_dev(int curve, int op, const void *d_a, const void *d_b, void *d_out, size_t n, void *stream);
+
+/* per-phase device timings (ms) of the last MSM on this thread: [digits+histogram, scan, scatter,
+ * bucket accumulate, bucket reduce, window combine, total]; and the window / counts it used. */
+int b200_msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds);
+/* kernel launches issued by this library since load (for bench.py's gpu_launches) */
+unsigned long long b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALGEBRA_B200_H */

@@ -1,0 +1,217 @@
+"""GPU parity of the MSM through the C ABI / the VariableBaseMSM mirror: results compared after into_affine(),
+limb-exact, against the oracle (naive sum, reference-algorithm restatement) and the reference's golden i*G table.
+Mirrors test-templates/src/msm.rs:17-72 (random and mixed-size scalars), plus the adversarial cases the reference
+formulas handle but its tests never generate: identity bases, repeated bases, P and -P in one
+bucket, zero scalars; window sweep; BN254; full-size checks via the identity  MSM(b_i*G, s_i) = (sum s_i*b_i)*G."""
+import ctypes
+import os
+import random
+
+import numpy as np
+import pytest
+
+import algebra_b200 as ab
+from algebra_b200 import _lib
+from algebra_b200 import msm as M
+from oracle import coracle as C
+from oracle import pyoracle as O
+
+from gpu_util import dev_empty, from_dev, stream, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_msm_affine(cid, bases, scalars, device=False):
+    if device:
+        xyz = ab.msm(cid, to_dev(bases), to_dev(scalars))
+    else:
+        xyz = ab.msm(cid, bases, scalars)
+    return ab.into_affine(cid, xyz)
+
+
+@pytest.fixture(scope="module")
+def g1_table(golden_dir):
+    return np.load(os.path.join(golden_dir, "bls12_381_g1_multiples.npy"))
+
+
+def table_affine(tab, idx):
+    """golden table rows (canonical limbs) -> Montgomery affine limbs"""
+    fq = O.BLS12_381_FQ
+    pts = []
+    for i in idx:
+        x, y = fq.from_limbs(tab[i, :6]), fq.from_limbs(tab[i, 6:])
+        pts.append(None if (x == 0 and y == 0) else (x, y))
+    return O.BLS12_381.encode_affine(pts), pts
+
+
+def test_kat_from_reference_table(g1_table):
+    """bases {i*G} from the reference fixture, small scalars: the answer is another fixture entry."""
+    cv, fr = O.BLS12_381, O.BLS12_381_FR
+    rnd = random.Random(5)
+    for trial in range(6):
+        k = rnd.randrange(1, 40)
+        idx = [rnd.randrange(0, 60) for _ in range(k)]          # includes 0*G = identity and repeats
+        sc = [rnd.randrange(0, 6) for _ in range(k)]
+        total = sum(i * s for i, s in zip(idx, sc))
+        if total >= 1000:
+            continue
+        bases, _ = table_affine(g1_table, idx)
+        want, _ = table_affine(g1_table, [total])
+        for c in (0, 3, 4, 7):
+            M.set_window(c)
+            assert (gpu_msm_affine(0, bases, fr.encode(sc)) == want[0]).all()
+        M.set_window(0)
+    # negative scalars (r - k) and cancellation to the identity
+    bases, _ = table_affine(g1_table, [10, 30, 7, 7])
+    sc = fr.encode([fr.p - 1, 2, 5, fr.p - 5])
+    want, _ = table_affine(g1_table, [50])
+    assert (gpu_msm_affine(0, bases, sc) == want[0]).all()
+    bases, _ = table_affine(g1_table, [7, 7])
+    assert (gpu_msm_affine(0, bases, fr.encode([5, fr.p - 5])) == 0).all()      # -> identity = (0,0)
+    xyz = ab.msm(0, bases, fr.encode([5, fr.p - 5]))
+    fq = O.BLS12_381_FQ
+    assert fq.from_limbs(xyz[:6]) == fq.R and fq.from_limbs(xyz[6:12]) == fq.R and not xyz[12:].any()  # Projective::zero()
+
+
+def test_api_errors_and_empty():
+    fr = O.BLS12_381_FR
+    b = np.zeros((3, 12), dtype=np.uint64)
+    s = np.zeros((2, 4), dtype=np.uint64)
+    with pytest.raises(ab.LengthMismatch) as e:
+        ab.msm(0, b, s)
+    assert e.value.min_len == 2                                   # Err(min_len), variable_base/mod.rs:73-77
+    assert (ab.into_affine(0, ab.msm(0, b[:0], s[:0])) == 0).all()   # empty -> zero
+    assert (ab.into_affine(0, M.msm_unchecked(0, b, s)) == 0).all()  # truncation, all-identity bases
+    out = np.zeros(18, dtype=np.uint64)
+    assert _lib.lib().b200_msm_sw_g1(9, b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), 2,
+                                     out.ctypes.data_as(ctypes.c_void_p)) == _lib.EINVAL
+    assert fr.bits == 255
+
+
+def synth(cid, n, seed):
+    """device-generated inputs: P_i = b_i*G, uniform scalars; returns device tensors + host copies"""
+    cv = O.CURVES[cid]
+    N = cv.fq.N
+    d_bases, d_b, d_s = dev_empty((n, 2 * N)), dev_empty((n,)), dev_empty((n, 4))
+    _lib.check(_lib.lib().b200_gen_bases_dev(cid, seed, n, d_bases.data_ptr(), d_b.data_ptr(), stream()))
+    _lib.check(_lib.lib().b200_gen_scalars_dev(cid, seed ^ 0xABCDEF, n, d_s.data_ptr(), stream()))
+    return d_bases, d_b, d_s
+
+
+def expected_from_b(cid, b_host, s_host):
+    """(sum_i s_i * b_i mod r) * G with Python ints"""
+    cv = O.CURVES[cid]
+    fr = cv.fr
+    sv = fr.decode(s_host)
+    tot = sum(int(b) * s for b, s in zip(b_host, sv)) % fr.p
+    return cv.encode_affine([cv.mul(cv.G, tot)])[0]
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+def test_generators_match_oracle(cid):
+    cv = O.CURVES[cid]
+    d_bases, d_b, d_s = synth(cid, 300, 42)
+    bh, bb, sh = from_dev(d_bases), from_dev(d_b), from_dev(d_s)
+    pts = cv.decode_affine(bh)
+    for i in list(range(20)) + [299]:
+        assert pts[i] == cv.mul(cv.G, int(bb[i])), i
+    assert all(cv.on_curve(p) for p in pts)
+    sv = [cv.fr.from_limbs(r) for r in sh]                  # raw limbs interpreted as Montgomery: must be < r
+    assert all(v < cv.fr.p for v in sv) and len(set(sv)) == 300
+
+
+@pytest.mark.parametrize("cid,n", [(0, 1 << 10), (1, 1 << 10), (0, 777), (0, 1), (0, 31), (0, 33)])
+def test_random_vs_naive_and_reference_algorithm(cid, n):
+    """test_var_base_msm (test-templates/src/msm.rs:17-32)"""
+    d_bases, d_b, d_s = synth(cid, n, 7 + n)
+    bh, sh = from_dev(d_bases), from_dev(d_s)
+    want = C.msm_naive(cid, bh, sh)
+    assert (C.msm_affine(cid, bh, sh, threads=8) == want).all()          # oracle self-consistency
+    assert (gpu_msm_affine(cid, bh, sh) == want).all()                    # host-buffer path
+    assert (gpu_msm_affine(cid, bh, sh, device=True) == want).all()       # device-resident path
+    assert (want == expected_from_b(cid, from_dev(d_b), sh)).all()
+
+
+def test_window_sweep():
+    cid, n = 0, 1 << 12
+    d_bases, d_b, d_s = synth(cid, n, 99)
+    want = expected_from_b(cid, from_dev(d_b), from_dev(d_s))
+    try:
+        for c in list(range(1, 17)) + [19, 21]:
+            M.set_window(c)
+            xyz = ab.msm(cid, d_bases, d_s)
+            assert (ab.into_affine(cid, xyz) == want).all(), c
+            assert M.last_timings()["c"] == c
+    finally:
+        M.set_window(0)
+
+
+def test_mixed_scalars_and_adversarial_bases():
+    """test_var_base_msm_mixed_scalars (msm.rs:36-72): every size class, +/-, shuffled; plus identity bases,
+    repeated bases, all-equal bases with equal scalars (doubling branch in one bucket), P/-P pairs."""
+    cid = 0
+    cv, fr = O.BLS12_381, O.BLS12_381_FR
+    rnd = random.Random(2024)
+    per = 256
+    sc = []
+    for bits in (1, 8, 16, 32, 64):
+        sc += [rnd.randrange(1 << bits) for _ in range(per)]
+        sc += [(fr.p - rnd.randrange(1 << bits)) % fr.p for _ in range(per)]
+    sc += [rnd.randrange(fr.p) for _ in range(per)]
+    rnd.shuffle(sc)
+    n = len(sc)
+    d_bases, d_b, _ = synth(cid, n, 555)
+    bh, bb = from_dev(d_bases).copy(), from_dev(d_b).copy().astype(object)
+    # adversarial edits
+    bh[5] = 0; bb[5] = 0                                    # identity base
+    bh[9] = bh[8]; bb[9] = bb[8]                            # repeated base
+    sc[9] = sc[8]                                           # ... with the same scalar -> same bucket -> doubling
+    neg8 = cv.decode_affine(bh[8:9])[0]
+    bh[11] = cv.encode_affine([cv.neg(neg8)])[0]; bb[11] = -int(bb[8])
+    sc[11] = sc[8]                                          # -P meets P (already doubled) in the same bucket
+    for i in range(100, 164):                               # 64 copies of one point with one scalar
+        bh[i] = bh[100]; bb[i] = bb[100]; sc[i] = sc[100]
+    sh = fr.encode(sc)
+    tot = sum(int(b) * s for b, s in zip(bb, sc)) % fr.p
+    want = cv.encode_affine([cv.mul(cv.G, tot)])[0]
+    assert (C.msm_affine(cid, bh, sh, threads=4) == want).all()
+    for c in (0, 4, 9, 13):
+        M.set_window(c)
+        assert (gpu_msm_affine(cid, bh, sh) == want).all(), c
+    M.set_window(0)
+    # all scalars zero / all bases identity
+    assert (gpu_msm_affine(cid, bh, np.zeros_like(sh)) == 0).all()
+    assert (gpu_msm_affine(cid, np.zeros_like(bh), sh) == 0).all()
+
+
+@pytest.mark.parametrize("cid,log_n", [(0, 16), (1, 16)])
+def test_config0_vs_reference_algorithm(cid, log_n):
+    """BASELINE configs[0]: n = 2^16 against the restated reference algorithm (c = 13, like ark_ec picks)."""
+    n = 1 << log_n
+    d_bases, d_b, d_s = synth(cid, n, 31337)
+    bh, sh = from_dev(d_bases), from_dev(d_s)
+    want = C.msm_affine(cid, bh, sh, threads=min(C.num_threads(), 32))
+    got = ab.into_affine(cid, ab.msm(cid, d_bases, d_s))
+    assert (got == want).all()
+    assert (want == expected_from_b(cid, from_dev(d_b), sh)).all()
+
+
+@pytest.mark.parametrize("cid,log_n", [(0, 20), (0, 22), (1, 22)])
+def test_large_sizes_by_linear_identity(cid, log_n):
+    """MSM(b_i*G, s_i) == (sum s_i*b_i mod r)*G — exact at any n without an O(n) CPU MSM."""
+    n = 1 << log_n
+    cv = O.CURVES[cid]
+    d_bases, d_b, d_s = synth(cid, n, 2718 + log_n)
+    sh, bb = from_dev(d_s), from_dev(d_b)
+    # sum s_i*b_i with numpy on 16-bit pieces (products < 2^32, sums of 2^22 terms < 2^54): exact
+    sm = sh.copy()                                           # Montgomery limbs -> canonical via the oracle REDC
+    canon = C.fp_op({0: 1, 1: 3}[cid], "into_bigint", sm)
+    s16 = canon.view(np.uint16).reshape(n, 16).astype(np.uint64)
+    b16 = bb.view(np.uint16).reshape(n, 4).astype(np.uint64)
+    tot = 0
+    for j in range(16):
+        for k in range(4):
+            tot += int(np.dot(s16[:, j], b16[:, k])) << (16 * (j + k))
+    want = cv.encode_affine([cv.mul(cv.G, tot % cv.fr.p)])[0]
+    got = ab.into_affine(cid, ab.msm(cid, d_bases, d_s))
+    assert (got == want).all()

@@ -3,8 +3,8 @@ variable-base MSM over short-Weierstrass G1 and the radix-2 NTT, behind the C AB
 This package is only the host-side mirror of the reference interfaces; all arithmetic runs in
 libalgebra_b200.so (hand-written CUDA).  No CPU fallback."""
 from . import _lib, params                                    # noqa: F401
-from .domain import Radix2EvaluationDomain                    # noqa: F401
-from .msm import LengthMismatch, into_affine, msm, msm_unchecked, sum_points   # noqa: F401
+from .radix2 import Radix2EvaluationDomain                    # noqa: F401
+from .variable_base import LengthMismatch, into_affine, msm, msm_unchecked, sum_points   # noqa: F401
 from .params import BLS12_381_G1, BN254_G1                    # noqa: F401
 
 __version__ = "0.1.0"

@@ -12,7 +12,7 @@ import pytest
 
 import algebra_b200 as ab
 from algebra_b200 import _lib
-from algebra_b200 import msm as M
+from algebra_b200 import variable_base as M
 from oracle import coracle as C
 from oracle import pyoracle as O
 

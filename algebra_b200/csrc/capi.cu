@@ -20,10 +20,12 @@ using namespace ab200;
 extern "C" {
 
 int b200_msm_sw_g1_dev(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     return msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, (cudaStream_t)stream);
 }
 
 int b200_msm_sw_g1(int curve, const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out_xyz) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
     if (!out_xyz || (n && (!bases || !scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
     if (n == 0) return msm_dispatch(curve, nullptr, nullptr, 0, out_xyz, 0);
@@ -46,10 +48,11 @@ int b200_msm_window_for(int curve, size_t n) {
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) return B200_EINVAL;
     return msm_auto_window(n, curve == B200_CURVE_BLS12_381 ? 255 : 254);
 }
-int b200_g1_sum(int curve, const uint64_t *points_xyz, size_t k, uint64_t *out_xyz) { return g1_sum_dispatch(curve, points_xyz, k, out_xyz, false); }
-int b200_g1_into_affine(int curve, const uint64_t *xyz, uint64_t *out_xy) { return g1_sum_dispatch(curve, xyz, 1, out_xy, true); }
+int b200_g1_sum(int curve, const uint64_t *points_xyz, size_t k, uint64_t *out_xyz) { if (int irc = ensure_device_init()) return irc; return g1_sum_dispatch(curve, points_xyz, k, out_xyz, false); }
+int b200_g1_into_affine(int curve, const uint64_t *xyz, uint64_t *out_xy) { if (int irc = ensure_device_init()) return irc; return g1_sum_dispatch(curve, xyz, 1, out_xy, true); }
 
 int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset_offset, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     int rc = ntt_dispatch(field, d_data, log_n, inverse, coset_offset, (cudaStream_t)stream);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -57,6 +60,7 @@ int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const 
 }
 
 int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const uint64_t *coset_offset) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     if (!data) { set_last_error("null data pointer"); return B200_EINVAL; }
     if (field != B200_FIELD_BLS12_381_FR && field != B200_FIELD_BN254_FR) { set_last_error("unknown scalar field id"); return B200_EINVAL; }
     if (log_n > (uint32_t)(field == B200_FIELD_BLS12_381_FR ? 32 : 28)) {
@@ -81,24 +85,28 @@ int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const ui
 int b200_clear_cache(void) { return ntt_clear_cache(); }
 
 int b200_gen_bases_dev(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     int rc = gen_bases_dispatch(curve, seed, n, d_bases, d_b, (cudaStream_t)stream);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 int b200_gen_scalars_dev(int field, uint64_t seed, size_t n, void *d_scalars, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     int rc = gen_scalars_dispatch(field, seed, n, d_scalars, (cudaStream_t)stream);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 int b200_fp_op_dev(int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n, int reps, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     int rc = fp_op_dispatch(field, op, d_a, d_b, d_out, n, reps, (cudaStream_t)stream);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
 int b200_ec_op_dev(int curve, int op, const void *d_a, const void *d_b, void *d_out, size_t n, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
     int rc = ec_op_dispatch(curve, op, d_a, d_b, d_out, n, (cudaStream_t)stream);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));

@@ -12,6 +12,9 @@
 namespace ab200 {
 
 void set_last_error(const std::string &msg);
+// once per device: keep freed stream-ordered allocations in the pool (default release threshold 0 gives the memory back at
+// every synchronisation, and re-allocating GBs per call costs tens of ms)
+int ensure_device_init();
 extern std::atomic<unsigned long long> g_launches;
 
 inline int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {

@@ -94,10 +94,18 @@ class Radix2EvaluationDomain:
             out[:k] = x[:k]
             return out
         x = np.asarray(x, dtype=np.uint64).reshape(-1, 4)
+        if x.shape[0] == n and x.flags["C_CONTIGUOUS"]:
+            return x
         out = np.zeros((n, 4), dtype=np.uint64)
         k = min(n, x.shape[0])
         out[:k] = x[:k]
         return out
+
+    @staticmethod
+    def _shares(x, orig) -> bool:
+        if _is_torch(x):
+            return _is_torch(orig) and x.data_ptr() == orig.data_ptr()
+        return isinstance(orig, np.ndarray) and np.shares_memory(x, orig)
 
     def _run(self, x, inverse: bool):
         keep, offp = self._offset_ptr()
@@ -118,13 +126,13 @@ class Radix2EvaluationDomain:
     def fft(self, coeffs):
         """EvaluationDomain::fft (poly/src/domain/mod.rs:94-98): returns a new vector of `size` evaluations."""
         x = self._resize(coeffs)
-        if x is coeffs or (_is_torch(x) and x.data_ptr() == coeffs.data_ptr()):
+        if self._shares(x, coeffs):
             x = x.clone() if _is_torch(x) else x.copy()
         return self._run(x, False)
 
     def ifft(self, evals):
         x = self._resize(evals)
-        if x is evals or (_is_torch(x) and x.data_ptr() == evals.data_ptr()):
+        if self._shares(x, evals):
             x = x.clone() if _is_torch(x) else x.copy()
         return self._run(x, True)
 

@@ -21,11 +21,13 @@
  *   - msm_signed's small-scalar size classes (:251-336) are folded into the signed-digit
  *     path (zero scalars are still filtered, :253); the sum is the same group element.
  */
+#define _GNU_SOURCE
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
 #include <pthread.h>
+#include <sched.h>
 #include <unistd.h>
 
 typedef uint64_t u64;
@@ -489,6 +491,16 @@ static void msm_window_range(size_t tlo, size_t thi, void *vp) {
     }
 }
 
+typedef struct { const field_t *fr; const u64 *scalars; u64 *big; int zeros; } prelude_ctx;
+static void prelude_range(size_t lo, size_t hi, void *vp) {
+    prelude_ctx *c = vp; int z = 0;
+    for (size_t i = lo; i < hi; i++) {
+        u64 t[MAXN]; memcpy(t, c->scalars + 4 * i, 32); fp_into_bigint(c->fr, t);
+        memcpy(c->big + 4 * i, t, 32); z |= is_zero(t, 4);
+    }
+    if (z) __atomic_store_n(&c->zeros, 1, __ATOMIC_RELAXED);
+}
+
 /* VariableBaseMSM::msm_unchecked (:59-64) -> msm_bigint_wnaf (:512-558) with `threads` rayon threads.
  * bases: n x 2N Montgomery limbs, scalars: n x 4 Montgomery Fr limbs; out: 3N Jacobian Montgomery limbs.
  * c_override > 0 forces the window size (for window sweeps); 0 = the reference's rule per chunk. */
@@ -497,13 +509,19 @@ int ark_msm(int curve, const u64 *bases, const u64 *scalars, size_t n, u64 *out,
     const field_t *f = cv.fq; int N = cv.N; size_t B = 8 * N;
     jac_t total; jac_set_zero(f, &total);
     if (threads < 1) threads = 1;
-    /* into_bigint (:60-62) + zero filter (msm_signed :253) */
-    u64 *big = malloc(n * 32 + 32); u64 *fb = malloc(n * 2 * B + 16);
-    size_t m = 0;
-    for (size_t i = 0; i < n; i++) {
-        u64 t[4]; memcpy(t, scalars + 4 * i, 32); fp_into_bigint(cv.fr, t);
-        if (is_zero(t, 4)) continue;
-        memcpy(big + 4 * m, t, 32); memcpy(fb + m * 2 * N, bases + i * 2 * N, 2 * B); m++;
+    /* into_bigint in parallel (cfg_iter, :60-62) + zero filter (msm_signed :253; compaction only if a zero exists) */
+    u64 *big = malloc(n * 32 + 32); u64 *fb = NULL;
+    prelude_ctx pc = {cv.fr, scalars, big, 0};
+    par_for(n, threads, 1 << 14, prelude_range, &pc);
+    size_t m = n;
+    const u64 *use_bases = bases;
+    if (pc.zeros) {
+        fb = malloc(n * 2 * B + 16); m = 0;
+        for (size_t i = 0; i < n; i++) {
+            if (is_zero(big + 4 * i, 4)) continue;
+            memmove(big + 4 * m, big + 4 * i, 32); memcpy(fb + m * 2 * N, bases + i * 2 * N, 2 * B); m++;
+        }
+        use_bases = fb;
     }
     if (m > 0) {
         size_t num_chunks = threads < 2 ? 1 : threads / 2;              /* :521-535 */
@@ -524,7 +542,7 @@ int ark_msm(int curve, const u64 *bases, const u64 *scalars, size_t n, u64 *out,
         }
         size_t ntasks = task_off[nchunks];
         xyzz_t *wsum = malloc(ntasks * sizeof(xyzz_t));
-        msm_ctx mc = {&cv, fb, big, m, chunk_size, nchunks, num_bits, cs, Ws, task_off, digs, wsum};
+        msm_ctx mc = {&cv, use_bases, big, m, chunk_size, nchunks, num_bits, cs, Ws, task_off, digs, wsum};
         par_for(nchunks, threads, 1, msm_digits_range, &mc);
         par_for(ntasks, threads, 1, msm_window_range, &mc);
         /* window combine per chunk (:489-502), then sum over chunks (:557) */
@@ -724,4 +742,19 @@ int ark_domain_params(int field, unsigned log_n, u64 *group_gen, u64 *group_gen_
     return 0;
 }
 
-int ark_num_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n < 1 ? 1 : (int)n; }
+/* usable hardware threads: affinity mask, capped by a cgroup-v2 CPU quota if one is set */
+int ark_num_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { int c = CPU_COUNT(&set); if (c > 0 && c < n) n = c; }
+    FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char q[64]; long period = 0;
+        if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            long quota = atol(q), c = (quota + period - 1) / period;
+            if (c > 0 && c < n) n = c;
+        }
+        fclose(f);
+    }
+    return n < 1 ? 1 : (int)n;
+}

@@ -1,5 +1,5 @@
 // msm.cu — variable-base MSM over short-Weierstrass G1 (a = 0) for sm_100a: bucket method (Pippenger) with
-// signed c-bit digits, counting-sort bucket assignment and thread-per-bucket XYZZ accumulation.
+// signed c-bit digits, counting-sort bucket assignment and task-balanced XYZZ accumulation.
 //
 // Replaces VariableBaseMSM::msm_unchecked for Projective<P> (ec/src/scalar_mul/variable_base/mod.rs:59-64
 // -> msm_bigint_wnaf_parallel :437-503).  Same mathematics, GPU schedule:
@@ -8,8 +8,8 @@
 //                                                       (window, |digit|) with global atomics
 //   buckets[|d|-1] +=/-= base  (:467-475)           ->  exclusive scan of the histogram, msm_digits_kernel<SCATTER>
 //                                                       writes (index | sign) into bucket-sorted order, then
-//                                                       msm_accumulate_kernel: one thread per (window, bucket) runs the
-//                                                       reference's `Bucket += Affine` (bucket.rs:168-238) over its run
+//                                                       msm_accumulate_kernel: one thread per task of T sorted entries runs the
+//                                                       reference's `Bucket += Affine` (bucket.rs:168-238), flushing per bucket
 //   running-sum  res += running_sum (:478-484)      ->  msm_bucket_reduce_kernel: each thread does the running sum over a
 //                                                       chunk of m buckets plus (chunk offset) * (chunk total);
 //                                                       msm_sum_partials_kernel tree-adds the chunks of a window
@@ -60,7 +60,7 @@ static MsmGeom make_geom(int c, int scalar_bits) {
 // digits: canonical scalar -> signed digits (make_digits, :754-794); MODE 0 = histogram, 1 = scatter
 // ------------------------------------------------------------------------------------------------
 template <class C, int MODE>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restrict__ scalars, size_t n, MsmGeom g,
+__global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restrict__ scalars, size_t n, MsmGeom g, int w_lo, int w_hi,
                                                          uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
     using FR = Fp<typename C::Fr>;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restr
     const int c = g.c;
     const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < g.W; w++) {
+    for (int w = 0; w < w_hi; w++) {  // the carry chain needs every lower window; only [w_lo, w_hi) is emitted
         const int bit = w * c, wi = bit >> 5, sh = bit & 31;
         uint64_t two = ((uint64_t)k[wi + 1] << 32) | k[wi];
         uint32_t coef = ((uint32_t)(two >> sh) & mask) + carry;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restr
             if (carry) { mag = (1u << c) - coef; neg = 1; }  // digit = coef - 2^c in [-2^(c-1), 0)
             else mag = coef;
         }
-        if (mag) {
+        if (mag && w >= w_lo) {
             uint32_t gid = (uint32_t)w * g.nb + (mag - 1);
             if (MODE == 0) {
                 atomicAdd(&counts_or_cursor[gid], 1u);
@@ -173,36 +173,72 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// bucket accumulation: one thread per (window, bucket); the hot loop (Bucket += Affine, bucket.rs:168-238)
+// bucket accumulation — the hot loop (Bucket += Affine, bucket.rs:168-238), balanced by construction:
+// the bucket-sorted entry array is cut into tasks of exactly T consecutive entries, one thread per task, whatever the
+// bucket sizes are (a scalar distribution that piles everything into one bucket, or a short top window with 8 buckets
+// holding n/8 points each, costs the same as the uniform case).  A thread walks its slice and flushes an accumulator at
+// every bucket boundary: buckets that begin and end inside the slice are written straight to `buckets`; the piece of a
+// bucket that began in an earlier task goes to head[t], the piece of a bucket that continues into the next task to tail[t].
+// msm_fixup_* then add tail[t0] + head[t0+1..t1] for every bucket that spans tasks.  `buckets` is pre-zeroed (zz = zzz = 0
+// is the XYZZ identity) so empty buckets need no writer.
 // ------------------------------------------------------------------------------------------------
+static constexpr uint32_t kNoBucket = 0xffffffffu;
+
+template <class P> __device__ __forceinline__ void store_xyzz(uint32_t *p, const Xyzz<P> &b);
+template <class P> __device__ __forceinline__ void load_xyzz(Xyzz<P> &b, const uint32_t *p);
+
 template <class C>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                             const uint32_t *__restrict__ offsets, uint32_t total_buckets,
-                                                             uint32_t *__restrict__ buckets) {
+                                                             const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t T,
+                                                             uint32_t *__restrict__ buckets, uint32_t *__restrict__ head,
+                                                             uint32_t *__restrict__ tail, uint32_t *__restrict__ head_bucket,
+                                                             uint32_t *__restrict__ tail_bucket, uint32_t num_tasks) {
     using P = typename C::Fq;
     using E = Ec<P>;
     constexpr int L = P::L;
-    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total_buckets) return;
-    uint32_t k = offsets[gid];
-    const uint32_t end = offsets[gid + 1];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tasks) return;
+    const uint32_t M = __ldg(offsets + total_buckets);
+    const uint64_t lo64 = (uint64_t)t * T;
+    if (lo64 >= M) {
+        head_bucket[t] = kNoBucket;
+        tail_bucket[t] = kNoBucket;
+        return;
+    }
+    const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min((uint64_t)M, lo64 + T);
+    // b = last index with offsets[b] <= lo  (=> offsets[b] <= lo < offsets[b+1])
+    uint32_t bl = 0, br = total_buckets;  // invariant: offsets[bl] <= lo, offsets[br] > lo (offsets[total] = M > lo)
+    while (br - bl > 1) {
+        uint32_t mid = bl + ((br - bl) >> 1);
+        if (__ldg(offsets + mid) <= lo) bl = mid; else br = mid;
+    }
+    uint32_t b = bl, bucket_end = __ldg(offsets + b + 1);
+    bool started_before = __ldg(offsets + b) < lo;
+    uint32_t hb = kNoBucket;
+
     typename E::B acc;
     E::xyzz_set_zero(acc);
     uint32_t cx[L], cy[L], nx[L], ny[L];
-    uint32_t e = 0, e_next = 0;
-    if (k < end) {
-        e = __ldg(sorted + k);
+    uint32_t e = __ldg(sorted + lo), e_next = 0;
+    {
         const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
         load_limbs_nc<L>(cx, bp);
         load_limbs_nc<L>(cy, bp + L);
     }
-    while (k < end) {
-        const bool more = (k + 1 < end);
+    for (uint32_t pos = lo; pos < hi; pos++) {
+        const bool more = (pos + 1 < hi);
         if (more) {  // issue the next gather before the ~10 modmuls of this addition
-            e_next = __ldg(sorted + k + 1);
+            e_next = __ldg(sorted + pos + 1);
             const uint32_t *bp = bases + (size_t)(e_next & 0x7fffffffu) * (2 * L);
             load_limbs_nc<L>(nx, bp);
             load_limbs_nc<L>(ny, bp + L);
+        }
+        if (pos == bucket_end) {  // bucket b is complete: flush, move to the (non-empty) bucket that owns `pos`
+            if (started_before) { store_xyzz<P>(head + (size_t)t * (4 * L), acc); hb = b; }
+            else store_xyzz<P>(buckets + (size_t)b * (4 * L), acc);
+            E::xyzz_set_zero(acc);
+            started_before = false;
+            do { b++; bucket_end = __ldg(offsets + b + 1); } while (bucket_end <= pos);
         }
         E::madd(acc, cx, cy, (e >> 31) != 0);
         if (more) {
@@ -210,13 +246,82 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__r
             limbs_copy<L>(cy, ny);
             e = e_next;
         }
-        k++;
     }
-    uint32_t *o = buckets + (size_t)gid * (4 * L);
-    store_limbs<L>(o, acc.x);
-    store_limbs<L>(o + L, acc.y);
-    store_limbs<L>(o + 2 * L, acc.zz);
-    store_limbs<L>(o + 3 * L, acc.zzz);
+    uint32_t tb = kNoBucket;
+    if (bucket_end == hi) {  // the last bucket ends exactly with the slice
+        if (started_before) { store_xyzz<P>(head + (size_t)t * (4 * L), acc); hb = b; }
+        else store_xyzz<P>(buckets + (size_t)b * (4 * L), acc);
+    } else if (started_before) {  // the whole slice is an inner piece of one bucket
+        store_xyzz<P>(head + (size_t)t * (4 * L), acc);
+        hb = b;
+    } else {
+        store_xyzz<P>(tail + (size_t)t * (4 * L), acc);
+        tb = b;
+    }
+    head_bucket[t] = hb;
+    tail_bucket[t] = tb;
+}
+
+// bucket b = tail[t0] + head[t0+1] + ... + head[t1], t1 = task holding the bucket's last entry.
+// small spans: one thread per task boundary; long spans (heavy buckets): one block per bucket.
+static constexpr uint32_t kFixupSmall = 16;
+template <class C>
+__global__ void __launch_bounds__(128) msm_fixup_small_kernel(const uint32_t *__restrict__ offsets, uint32_t T, const uint32_t *__restrict__ head,
+                                                              const uint32_t *__restrict__ tail, const uint32_t *__restrict__ tail_bucket,
+                                                              uint32_t num_tasks, uint32_t *__restrict__ buckets) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tasks) return;
+    const uint32_t b = tail_bucket[t];
+    if (b == kNoBucket) return;
+    const uint32_t t1 = (__ldg(offsets + b + 1) - 1) / T;
+    if (t1 - t > kFixupSmall) return;
+    typename E::B acc, x;
+    load_xyzz<P>(acc, tail + (size_t)t * (4 * L));
+    for (uint32_t k = t + 1; k <= t1; k++) {
+        load_xyzz<P>(x, head + (size_t)k * (4 * L));
+        E::xyzz_add(acc, x);
+    }
+    store_xyzz<P>(buckets + (size_t)b * (4 * L), acc);
+}
+template <class C>
+__global__ void __launch_bounds__(128) msm_fixup_big_kernel(const uint32_t *__restrict__ offsets, uint32_t T, const uint32_t *__restrict__ head,
+                                                            const uint32_t *__restrict__ tail, const uint32_t *__restrict__ tail_bucket,
+                                                            uint32_t num_tasks, uint32_t *__restrict__ buckets) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    extern __shared__ uint32_t sm[];
+    const uint32_t t = blockIdx.x;
+    if (t >= num_tasks) return;
+    const uint32_t b = tail_bucket[t];
+    if (b == kNoBucket) return;
+    const uint32_t t1 = (__ldg(offsets + b + 1) - 1) / T;
+    if (t1 - t <= kFixupSmall) return;
+    typename E::B acc, x;
+    E::xyzz_set_zero(acc);
+    if (threadIdx.x == 0) load_xyzz<P>(acc, tail + (size_t)t * (4 * L));
+    for (uint32_t k = t + 1 + threadIdx.x; k <= t1; k += blockDim.x) {
+        load_xyzz<P>(x, head + (size_t)k * (4 * L));
+        E::xyzz_add(acc, x);
+    }
+    store_xyzz<P>(sm + threadIdx.x * (4 * L), acc);
+    __syncthreads();
+    for (uint32_t s2 = blockDim.x >> 1; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) {
+            load_xyzz<P>(acc, sm + threadIdx.x * (4 * L));
+            load_xyzz<P>(x, sm + (threadIdx.x + s2) * (4 * L));
+            E::xyzz_add(acc, x);
+            store_xyzz<P>(sm + threadIdx.x * (4 * L), acc);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        load_xyzz<P>(acc, sm);
+        store_xyzz<P>(buckets + (size_t)b * (4 * L), acc);
+    }
 }
 
 template <class P> __device__ __forceinline__ void load_xyzz(Xyzz<P> &b, const uint32_t *p) {
@@ -387,28 +492,28 @@ int msm_set_window(int c) {
     return 0;
 }
 
-// Cost model (Fq modmuls): accumulation 10 per (point, window) inflated by the expected slowest-lane excess of a warp
-// of Poisson(lambda) bucket loads, reduction ~30 per bucket (two XYZZ adds + scalar-multiple overhead).
+// Window choice: a time model fitted to the B200 sweep committed in profiles/r01_window_sweep.jsonl (n = 2^26, BLS12-381):
+//   accumulation 0.39 ns per (point, window) [x L^2 scaling for the 8-limb curve], reduction 2.6 ns per bucket,
+//   scatter + histogram 0.02 ns per entry, + contention when the top window has fewer than ~2^10 buckets.
 int msm_auto_window(size_t n, int scalar_bits) {
     if (n < 32) return 3;  // same floor as the reference (:445-449)
     double best = 1e300;
     int best_c = 3;
-    for (int c = 4; c <= 22; c++) {
+    for (int c = 4; c <= 23; c++) {
         MsmGeom g = make_geom(c, scalar_bits);
         if ((double)g.total_buckets * 192.0 > 24e9) continue;
-        double lambda = (double)n / (double)g.nb;
-        double imbalance = 1.0 + 2.2 / std::sqrt(lambda + 1.0);
-        double acc = 10.0 * (double)n * g.W * imbalance;
-        double red = 30.0 * (double)g.total_buckets;
-        // very small buckets-per-window counts starve the GPU: need ~150k threads to fill 148 SMs
-        double par = (double)g.total_buckets < 150000.0 ? 150000.0 / (double)g.total_buckets : 1.0;
-        double cost = acc * std::min(par, 8.0) + red;
-        if (cost < best) { best = cost; best_c = c; }
+        const double entries = (double)n * g.W;
+        double t = 0.39 * entries + 2.6 * (double)g.total_buckets + 0.02 * entries;
+        if (g.top_bits < 10) t += 0.15 * (double)n;   // hot top-window buckets serialise the atomics
+        // tiny inputs: keep enough accumulation tasks (>= 8 entries each) to fill the machine
+        t += 2000.0 * g.W;                             // per-window fixed costs (reduction tree, combine doublings)
+        if (t < best) { best = t; best_c = c; }
     }
     return best_c;
 }
 
-template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d_scalars, size_t n, uint32_t *d_out, cudaStream_t st) {
+template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d_scalars, size_t n, uint32_t *d_out, cudaStream_t st,
+                                      cudaEvent_t bases_ready) {
     constexpr int L = C::Fq::L;
     if (n >= ((size_t)1 << 31)) { set_last_error("n must be < 2^31"); return B200_ETOOLARGE; }
     const int c = t_window_override ? t_window_override : msm_auto_window(n, C::SCALAR_BITS);
@@ -428,6 +533,15 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     AB_CUDA(cudaMallocAsync(&sorted, std::max<size_t>(max_entries, 1) * 4, st));
     AB_CUDA(cudaMallocAsync(&block_totals, scan_blocks * 4, st));
     AB_CUDA(cudaMallocAsync(&buckets, nb_total * 4 * L * 4, st));
+    // accumulation tasks: T consecutive sorted entries per thread (>= ~128k tasks when the input allows it)
+    uint32_t T = 512;
+    while (T > 8 && max_entries / T < (1u << 17)) T >>= 1;
+    const uint32_t num_tasks = (uint32_t)((max_entries + T - 1) / T);
+    uint32_t *head = nullptr, *tail = nullptr, *head_bucket = nullptr, *tail_bucket = nullptr;
+    AB_CUDA(cudaMallocAsync(&head, (size_t)std::max(num_tasks, 1u) * 4 * L * 4, st));
+    AB_CUDA(cudaMallocAsync(&tail, (size_t)std::max(num_tasks, 1u) * 4 * L * 4, st));
+    AB_CUDA(cudaMallocAsync(&head_bucket, (size_t)std::max(num_tasks, 1u) * 4, st));
+    AB_CUDA(cudaMallocAsync(&tail_bucket, (size_t)std::max(num_tasks, 1u) * 4, st));
     // reduction geometry: chunk of m = 2^log_m buckets per thread
     int log_m = 5;
     while (log_m > 0 && (g.nb >> log_m) < 64) log_m--;
@@ -439,7 +553,7 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     AB_CUDA(cudaEventRecord(ev[0], st));
     AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
     const unsigned dblocks = (unsigned)((n + 255) / 256);
-    msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(d_scalars, n, g, counts, nullptr);
+    msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(d_scalars, n, g, 0, g.W, counts, nullptr);
     AB_LAUNCHED();
     AB_CUDA(cudaEventRecord(ev[1], st));
     scan_block_totals_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals);
@@ -450,11 +564,28 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     AB_LAUNCHED();
     AB_CUDA(cudaMemcpyAsync(cursor, offsets, nb_total * 4, cudaMemcpyDeviceToDevice, st));
     AB_CUDA(cudaEventRecord(ev[2], st));
-    msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(d_scalars, n, g, cursor, sorted);
-    AB_LAUNCHED();
+    // scatter in groups of windows so that the active write fronts (one 32-byte sector per bucket of the group) stay
+    // L2-resident: random 4-byte stores into a multi-GB array otherwise cost a DRAM sector each (measured 2.5x slower)
+    {
+        const size_t front_bytes = (size_t)g.nb * 32;
+        int group = (int)std::max<size_t>(1, ((size_t)48 << 20) / front_bytes);
+        for (int w0 = 0; w0 < g.W; w0 += group) {
+            msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(d_scalars, n, g, w0, std::min(g.W, w0 + group), cursor, sorted);
+            AB_LAUNCHED();
+        }
+    }
     AB_CUDA(cudaEventRecord(ev[3], st));
-    msm_accumulate_kernel<C><<<(unsigned)((nb_total + 127) / 128), 128, 0, st>>>(d_bases, sorted, offsets, (uint32_t)nb_total, buckets);
-    AB_LAUNCHED();
+    AB_CUDA(cudaMemsetAsync(buckets, 0, nb_total * 4 * L * 4, st));
+    if (bases_ready) AB_CUDA(cudaStreamWaitEvent(st, bases_ready, 0));  // host path: bases still streaming in while we sorted
+    if (num_tasks) {
+        msm_accumulate_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, (uint32_t)nb_total, T, buckets, head, tail,
+                                                                        head_bucket, tail_bucket, num_tasks);
+        AB_LAUNCHED();
+        msm_fixup_small_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, buckets);
+        AB_LAUNCHED();
+        msm_fixup_big_kernel<C><<<num_tasks, 128, 128 * 4 * L * 4, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, buckets);
+        AB_LAUNCHED();
+    }
     AB_CUDA(cudaEventRecord(ev[4], st));
     const unsigned rthreads = (unsigned)g.W * chunks;
     msm_bucket_reduce_kernel<C><<<(rthreads + 127) / 128, 128, 0, st>>>(buckets, g, log_m, chunks, partials);
@@ -468,7 +599,7 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
 
     uint32_t total_entries = 0;
     AB_CUDA(cudaMemcpyAsync(&total_entries, offsets + nb_total, 4, cudaMemcpyDeviceToHost, st));
-    for (uint32_t *p : {counts, offsets, cursor, sorted, block_totals, buckets, partials, window_sums}) AB_CUDA(cudaFreeAsync(p, st));
+    for (uint32_t *p : {counts, offsets, cursor, sorted, block_totals, buckets, partials, window_sums, head, tail, head_bucket, tail_bucket}) AB_CUDA(cudaFreeAsync(p, st));
     AB_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 6; i++) AB_CUDA(cudaEventElapsedTime(&t_last.ms[i], ev[i], ev[i + 1]));
     AB_CUDA(cudaEventElapsedTime(&t_last.ms[6], ev[0], ev[6]));
@@ -479,7 +610,7 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     return 0;
 }
 
-int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st) {
+int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, cudaEvent_t bases_ready) {
     if (!out_xyz_host || (n && (!d_bases || !d_scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
     const int L = curve == B200_CURVE_BLS12_381 ? 12 : 8;
@@ -493,8 +624,8 @@ int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n
     }
     uint32_t *d_out = nullptr;
     AB_CUDA(cudaMallocAsync(&d_out, 3 * L * 4, st));
-    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st)
-                                           : msm_run<CurveBn>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st);
+    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, bases_ready)
+                                           : msm_run<CurveBn>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, bases_ready);
     if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(out_xyz_host, d_out, 3 * L * 4, cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaFreeAsync(d_out, st));

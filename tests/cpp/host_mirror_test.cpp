@@ -1,0 +1,33 @@
+// CPU test of the C++ host mirror (include/algebra_b200.hpp): domain construction / coset / element logic and the MSM
+// length-mismatch contract.  Prints values that tests/test_cpp_mirror.py compares with the oracle.  No GPU needed for the
+// printed part; with `gpu` as argv[1] it also runs one tiny MSM + NTT through the mirror.
+#include <cstdio>
+#include <cstring>
+#include "../../include/algebra_b200.hpp"
+using namespace ab200;
+static void print(const char *name, const Fr &v) {
+    printf("%s %016lx%016lx%016lx%016lx\n", name, (unsigned long)v[3], (unsigned long)v[2], (unsigned long)v[1], (unsigned long)v[0]);
+}
+int main(int argc, char **argv) {
+    auto d = Radix2EvaluationDomain<Bls12_381G1>::make(1000).value();
+    printf("size %lu log %u\n", (unsigned long)d.size, d.log_size_of_group);
+    print("group_gen", d.group_gen); print("group_gen_inv", d.group_gen_inv); print("size_inv", d.size_inv);
+    Fr off = d.size_as_field_element;  // 1024 as a field element: a non-trivial offset
+    auto c = d.get_coset(off).value();
+    print("offset", c.offset); print("offset_inv", c.offset_inv); print("offset_pow_size", c.offset_pow_size); print("element5", c.element(5));
+    printf("too_big %d\n", (int)Radix2EvaluationDomain<Bls12_381G1>::make(((size_t)1 << 32) + 1).has_value());
+    printf("bn_too_big %d\n", (int)Radix2EvaluationDomain<Bn254G1>::make(((size_t)1 << 28) + 1).has_value());
+    std::vector<Affine<Bls12_381G1>> bases(3); std::vector<Fr> scalars(2);
+    auto r = VariableBaseMSM<Bls12_381G1>::msm(bases, scalars);
+    printf("mismatch_err %d min_len %zu\n", (int)std::holds_alternative<size_t>(r), std::get<size_t>(r));
+    if (argc > 1 && !strcmp(argv[1], "gpu")) {
+        scalars.resize(3);
+        auto p = std::get<0>(VariableBaseMSM<Bls12_381G1>::msm(bases, scalars));   // identity bases -> identity
+        printf("gpu_msm_identity %d\n", (int)(p.z == Fq<Bls12_381G1>{}));
+        std::vector<Fr> v(8, d.size_inv);
+        auto dom8 = Radix2EvaluationDomain<Bls12_381G1>::make(8).value();
+        auto w = dom8.ifft(dom8.fft(v));
+        printf("gpu_ntt_roundtrip %d\n", (int)(w == v));
+    }
+    return 0;
+}

@@ -215,3 +215,30 @@ def test_large_sizes_by_linear_identity(cid, log_n):
     want = cv.encode_affine([cv.mul(cv.G, tot % cv.fr.p)])[0]
     got = ab.into_affine(cid, ab.msm(cid, d_bases, d_s))
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("c", [0, 6, 11, 18])
+def test_heavy_buckets_and_short_top_window(c):
+    """Skewed bucket loads: all scalars equal (every point of a window lands in ONE bucket, which then spans many
+    accumulation tasks -> head/tail partials and both fix-up kernels), and windows whose top digit has only a few
+    bits (c = 18: 3 top bits -> 8 buckets hold all n points).  Answer: s * sum(b_i) * G."""
+    cid, n = 0, 1 << 14
+    cv, fr = O.BLS12_381, O.BLS12_381_FR
+    d_bases, d_b, _ = synth(cid, n, 4242)
+    bb = [int(x) for x in from_dev(d_b)]
+    rnd = random.Random(c)
+    try:
+        M.set_window(c)
+        for s in (rnd.randrange(fr.p), fr.p - 1, 3):
+            sh = np.repeat(fr.encode([s]), n, axis=0)
+            want = cv.encode_affine([cv.mul(cv.G, s * sum(bb) % fr.p)])[0]
+            got = ab.into_affine(cid, ab.msm(cid, d_bases, to_dev(sh)))
+            assert (got == want).all(), (c, s)
+        # two scalar values only, interleaved
+        s1, s2 = rnd.randrange(fr.p), rnd.randrange(fr.p)
+        sh = np.tile(fr.encode([s1, s2]), (n // 2, 1))
+        tot = (s1 * sum(bb[0::2]) + s2 * sum(bb[1::2])) % fr.p
+        want = cv.encode_affine([cv.mul(cv.G, tot)])[0]
+        assert (ab.into_affine(cid, ab.msm(cid, d_bases, to_dev(sh))) == want).all()
+    finally:
+        M.set_window(0)

@@ -5,7 +5,8 @@
 namespace ab200 {
 int ntt_dispatch(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset, cudaStream_t st);
 int ntt_clear_cache();
-int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, cudaEvent_t bases_ready);
+int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, int K, const size_t *chunk_off,
+                 const cudaEvent_t *ready);
 int msm_set_window(int c);
 int msm_auto_window(size_t n, int scalar_bits);
 int msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds);
@@ -21,17 +22,18 @@ extern "C" {
 
 int b200_msm_sw_g1_dev(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz, void *stream) {
     { int irc = ensure_device_init(); if (irc) return irc; }
-    return msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, (cudaStream_t)stream, nullptr);
+    return msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, (cudaStream_t)stream, 1, nullptr, nullptr);
 }
 
 int b200_msm_sw_g1(int curve, const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out_xyz) {
     { int irc = ensure_device_init(); if (irc) return irc; }
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
     if (!out_xyz || (n && (!bases || !scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
-    if (n == 0) return msm_dispatch(curve, nullptr, nullptr, 0, out_xyz, 0, nullptr);
+    if (n == 0) return msm_dispatch(curve, nullptr, nullptr, 0, out_xyz, 0, 1, nullptr, nullptr);
     const size_t N = curve == B200_CURVE_BLS12_381 ? 6 : 4;
-    // two streams: scalars go first on the compute stream (digits, histogram, scan and scatter need only them) while the
-    // 3x larger base array streams in on a copy stream; the accumulation waits on `bases_ready`
+    // Pipeline over K input chunks on two streams: the copy stream moves (scalars_k, bases_k) for k = 0..K-1 back to back,
+    // the compute stream sorts and accumulates chunk k as soon as it has landed (msm.cu: msm_run).  With pinned host
+    // memory the PCIe time of chunks 1..K-1 hides behind the arithmetic of the chunks before them.
     static thread_local cudaStream_t streams[64][2] = {};
     int dev = 0;
     AB_CUDA(cudaGetDevice(&dev));
@@ -41,24 +43,34 @@ int b200_msm_sw_g1(int curve, const uint64_t *bases, const uint64_t *scalars, si
         AB_CUDA(cudaStreamCreateWithFlags(&streams[dev][1], cudaStreamNonBlocking));
     }
     cudaStream_t st = streams[dev][0], copy_st = streams[dev][1];
+    const int K = n >= ((size_t)1 << 22) ? 4 : 1;
+    size_t off[5];
+    cudaEvent_t ready[4], alloc_done;
+    // growing chunks (1/8, 1/8, 1/4, 1/2): only the first, small transfer is exposed; every later one is shorter than the
+    // arithmetic of the chunk before it
+    static const int kEighths[5] = {0, 1, 2, 4, 8};
+    for (int k = 0; k <= K; k++) off[k] = K == 1 ? (size_t)k * n : n / 8 * kEighths[k];
+    off[K] = n;
     void *d_bases = nullptr, *d_scalars = nullptr;
-    cudaEvent_t alloc_done, bases_ready;
     AB_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
-    AB_CUDA(cudaEventCreateWithFlags(&bases_ready, cudaEventDisableTiming));
     AB_CUDA(cudaMallocAsync(&d_bases, n * 2 * N * 8, st));
     AB_CUDA(cudaMallocAsync(&d_scalars, n * 32, st));
     AB_CUDA(cudaEventRecord(alloc_done, st));
     AB_CUDA(cudaStreamWaitEvent(copy_st, alloc_done, 0));
-    AB_CUDA(cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    AB_CUDA(cudaMemcpyAsync(d_bases, bases, n * 2 * N * 8, cudaMemcpyHostToDevice, copy_st));
-    AB_CUDA(cudaEventRecord(bases_ready, copy_st));
-    int rc = msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, st, bases_ready);
+    for (int k = 0; k < K; k++) {
+        const size_t lo = off[k], cnt = off[k + 1] - off[k];
+        AB_CUDA(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+        AB_CUDA(cudaMemcpyAsync((char *)d_scalars + lo * 32, (const char *)scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice, copy_st));
+        AB_CUDA(cudaMemcpyAsync((char *)d_bases + lo * 2 * N * 8, (const char *)bases + lo * 2 * N * 8, cnt * 2 * N * 8, cudaMemcpyHostToDevice, copy_st));
+        AB_CUDA(cudaEventRecord(ready[k], copy_st));
+    }
+    int rc = msm_dispatch(curve, d_bases, d_scalars, n, out_xyz, st, K, off, ready);
     cudaStreamSynchronize(copy_st);
     cudaFreeAsync(d_bases, st);
     cudaFreeAsync(d_scalars, st);
     cudaStreamSynchronize(st);
     cudaEventDestroy(alloc_done);
-    cudaEventDestroy(bases_ready);
+    for (int k = 0; k < K; k++) cudaEventDestroy(ready[k]);
     return rc;
 }
 

@@ -243,7 +243,8 @@ template <class P> struct Fp {
             }
             od[L - 1] = ptx::addc(od[L - 1], 0u);
         }
-        uint32_t m = ev[0] * P::INV32;
+        // m = T[0] * (-p^-1) mod 2^32; for moduli with p = 1 (mod 2^32) (BLS12-381 Fr) that is simply -T[0]
+        const uint32_t m = (P::INV32 == 0xffffffffu) ? (0u - ev[0]) : ev[0] * P::INV32;
         od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
         od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
 #pragma unroll
@@ -251,8 +252,13 @@ template <class P> struct Fp {
             od[j] = ptx::madc_lo_cc(P::MOD(j + 1), m, od[j]);
             od[j + 1] = ptx::madc_hi_cc(P::MOD(j + 1), m, od[j + 1]);
         }
-        ev[0] = ptx::mad_lo_cc(P::MOD(0), m, ev[0]);
-        ev[1] = ptx::madc_hi_cc(P::MOD(0), m, ev[1]);
+        if (P::MOD(0) == 1u) {  // p[0] = 1: the product m*p[0] is m itself — an add instead of a wide MAD
+            ev[0] = ptx::add_cc(ev[0], m);
+            ev[1] = ptx::addc_cc(ev[1], 0u);
+        } else {
+            ev[0] = ptx::mad_lo_cc(P::MOD(0), m, ev[0]);
+            ev[1] = ptx::madc_hi_cc(P::MOD(0), m, ev[1]);
+        }
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             ev[j] = ptx::madc_lo_cc(P::MOD(j), m, ev[j]);
@@ -280,7 +286,122 @@ template <class P> struct Fp {
         reduce_once(t);
         limbs_copy<L>(r, t);
     }
-    static AB_HD void sqr(uint32_t *r, const uint32_t *a) { mul(r, a, a); }  // asm path does the same (ff-asm/src/lib.rs:132)
+    // square_in_place (montgomery_backend.rs:248-317).  Measured on B200: the symmetric squaring below (sqr_sos, 234 instead
+    // of 300 wide MADs for L = 12) made msm_accumulate_kernel 2 % SLOWER (338 -> 345 ms @2^26: three 2L-word temporaries
+    // raise register pressure and the extra carry-ripple adds cost issue slots), so sqr stays mul(a, a) — which is also what
+    // the reference's asm path does (ff-asm/src/lib.rs:132).  sqr_sos is kept, tested, for latency-bound single-thread code.
+    static AB_HD void sqr(uint32_t *r, const uint32_t *a) { mul(r, a, a); }
+
+    // Symmetric squaring: t = a^2 by symmetry (L(L-1)/2 off-diagonal products, doubled, + L diagonal squares) followed by
+    // L word-serial reduction rows.  Same value as mul(a, a).
+    static AB_HD void sqr_sos(uint32_t *r, const uint32_t *a) {
+        // ---- off-diagonal sum S = sum_{i<j} a_i a_j 2^(32(i+j)), split by the parity of i+j into two carry-chain grids
+        uint32_t E[2 * L], O[2 * L];  // E: pairs (2k, 2k+1); O: pairs (2k+1, 2k+2)
+#pragma unroll
+        for (int i = 0; i < 2 * L; i++) { E[i] = 0u; O[i] = 0u; }
+#pragma unroll
+        for (int i = 0; i < L - 1; i++) {
+            // i + j odd  -> O grid: j = i+1, i+3, ...
+            {
+                int w = 0;
+                bool first = true;
+#pragma unroll
+                for (int j = i + 1; j < L; j += 2) {
+                    w = i + j;
+                    O[w] = first ? ptx::mad_lo_cc(a[i], a[j], O[w]) : ptx::madc_lo_cc(a[i], a[j], O[w]);
+                    O[w + 1] = ptx::madc_hi_cc(a[i], a[j], O[w + 1]);
+                    first = false;
+                }
+                if (w + 2 < 2 * L) O[w + 2] = ptx::addc(O[w + 2], 0u);  // the word above this row's chain is still zero
+            }
+            // i + j even -> E grid: j = i+2, i+4, ...
+            if (i + 2 < L) {
+                int w = 0;
+                bool first = true;
+#pragma unroll
+                for (int j = i + 2; j < L; j += 2) {
+                    w = i + j;
+                    E[w] = first ? ptx::mad_lo_cc(a[i], a[j], E[w]) : ptx::madc_lo_cc(a[i], a[j], E[w]);
+                    E[w + 1] = ptx::madc_hi_cc(a[i], a[j], E[w + 1]);
+                    first = false;
+                }
+                if (w + 2 < 2 * L) E[w + 2] = ptx::addc(E[w + 2], 0u);
+            }
+        }
+        // ---- t = 2*(E + O) + sum_i a_i^2 2^(64 i)
+        uint32_t t[2 * L];
+        t[0] = ptx::add_cc(E[0], O[0]);
+#pragma unroll
+        for (int i = 1; i < 2 * L - 1; i++) t[i] = ptx::addc_cc(E[i], O[i]);
+        t[2 * L - 1] = ptx::addc(E[2 * L - 1], O[2 * L - 1]);
+        t[0] = ptx::add_cc(t[0], t[0]);
+#pragma unroll
+        for (int i = 1; i < 2 * L - 1; i++) t[i] = ptx::addc_cc(t[i], t[i]);
+        t[2 * L - 1] = ptx::addc(t[2 * L - 1], t[2 * L - 1]);
+        t[0] = ptx::mad_lo_cc(a[0], a[0], t[0]);
+        t[1] = ptx::madc_hi_cc(a[0], a[0], t[1]);
+#pragma unroll
+        for (int i = 1; i < L; i++) {
+            t[2 * i] = ptx::madc_lo_cc(a[i], a[i], t[2 * i]);
+            t[2 * i + 1] = (i == L - 1) ? ptx::madc_hi(a[i], a[i], t[2 * i + 1]) : ptx::madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+        }
+        redc_wide(r, t);
+    }
+
+    // One reduction row on the split accumulators (cf. mont_row): T = (T + m*p) >> 32 with m = T[0]*INV, then the next
+    // high word of the 2L-word input enters at the top.  FIRST: ev = low words, od = 0, nothing to shift in yet.
+    template <bool FIRST> static AB_HD void redc_row(uint32_t *ev, uint32_t *od, uint32_t hi_word) {
+        if (!FIRST) {
+            ev[0] = ptx::add_cc(ev[0], od[1]);
+#pragma unroll
+            for (int j = 0; j < L - 2; j++) od[j] = ptx::addc_cc(od[j + 2], 0u);
+            od[L - 2] = ptx::addc_cc(hi_word, 0u);
+            od[L - 1] = ptx::addc(0u, 0u);
+        }
+        const uint32_t m = (P::INV32 == 0xffffffffu) ? (0u - ev[0]) : ev[0] * P::INV32;
+        od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
+        od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
+#pragma unroll
+        for (int j = 2; j < L; j += 2) {
+            od[j] = ptx::madc_lo_cc(P::MOD(j + 1), m, od[j]);
+            od[j + 1] = ptx::madc_hi_cc(P::MOD(j + 1), m, od[j + 1]);
+        }
+        if (P::MOD(0) == 1u) {
+            ev[0] = ptx::add_cc(ev[0], m);
+            ev[1] = ptx::addc_cc(ev[1], 0u);
+        } else {
+            ev[0] = ptx::mad_lo_cc(P::MOD(0), m, ev[0]);
+            ev[1] = ptx::madc_hi_cc(P::MOD(0), m, ev[1]);
+        }
+#pragma unroll
+        for (int j = 2; j < L; j += 2) {
+            ev[j] = ptx::madc_lo_cc(P::MOD(j), m, ev[j]);
+            ev[j + 1] = ptx::madc_hi_cc(P::MOD(j), m, ev[j + 1]);
+        }
+        od[L - 1] = ptx::addc(od[L - 1], 0u);
+    }
+
+    // r = t * R^-1 mod p for a 2L-word t < p*R (Montgomery reduction, separated from the multiplication)
+    static AB_HD void redc_wide(uint32_t *r, const uint32_t *t) {
+        uint32_t ev[L], od[L];
+#pragma unroll
+        for (int i = 0; i < L; i++) { ev[i] = t[i]; od[i] = 0u; }
+        redc_row<true>(ev, od, 0u);
+        redc_row<false>(od, ev, t[L]);
+#pragma unroll
+        for (int i = 2; i < L; i += 2) {
+            redc_row<false>(ev, od, t[L + i - 1]);
+            redc_row<false>(od, ev, t[L + i]);
+        }
+        // after an even number of rows: T = (od >> 32) + ev, plus the last high word at the top
+        uint32_t u[L];
+        u[0] = ptx::add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int i = 1; i < L - 1; i++) u[i] = ptx::addc_cc(ev[i], od[i + 1]);
+        u[L - 1] = ptx::addc(ev[L - 1], t[2 * L - 1]);
+        reduce_once(u);
+        limbs_copy<L>(r, u);
+    }
 
     // Montgomery -> canonical: multiply by the integer 1 (montgomery_backend.rs:392-412: N REDC rounds).
     static AB_HD void from_mont(uint32_t *r, const uint32_t *a) {

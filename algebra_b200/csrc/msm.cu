@@ -512,20 +512,51 @@ int msm_auto_window(size_t n, int scalar_bits) {
     return best_c;
 }
 
+// buckets[b] += extra[b]  (chunked host path: every chunk after the first accumulates into `extra`)
+template <class C>
+__global__ void __launch_bounds__(128) msm_merge_kernel(uint32_t *__restrict__ buckets, const uint32_t *__restrict__ extra, uint32_t total_buckets) {
+    using P = typename C::Fq;
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    typename E::B x, y;
+    load_xyzz<P>(y, extra + (size_t)b * (4 * L));
+    if (E::xyzz_is_zero(y)) return;
+    load_xyzz<P>(x, buckets + (size_t)b * (4 * L));
+    E::xyzz_add(x, y);
+    store_xyzz<P>(buckets + (size_t)b * (4 * L), x);
+}
+
+// One MSM = K input chunks (K = 1 for device-resident inputs).  Each chunk is digit-sorted and accumulated on its own as
+// soon as its `ready` event fires, so the host path overlaps the PCIe transfer of chunk k+1 with the arithmetic of chunk k;
+// chunk 0 accumulates straight into `buckets`, later chunks into a second array that is merged bucket-wise.  The bucket
+// reduction and window combine run once at the end.
+struct MsmChunks {
+    int K = 1;
+    const size_t *offset = nullptr;      // K+1 element offsets into bases / scalars
+    const cudaEvent_t *ready = nullptr;  // K events (or nullptr: data already resident)
+};
+
 template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d_scalars, size_t n, uint32_t *d_out, cudaStream_t st,
-                                      cudaEvent_t bases_ready) {
+                                      const MsmChunks &ch) {
     constexpr int L = C::Fq::L;
     if (n >= ((size_t)1 << 31)) { set_last_error("n must be < 2^31"); return B200_ETOOLARGE; }
     const int c = t_window_override ? t_window_override : msm_auto_window(n, C::SCALAR_BITS);
     const MsmGeom g = make_geom(c, C::SCALAR_BITS);
     const size_t nb_total = g.total_buckets;
-    const size_t max_entries = n * (size_t)g.W;
+    const size_t one_chunk[2] = {0, n};
+    const int K = ch.K > 1 ? ch.K : 1;
+    const size_t *coff = K > 1 ? ch.offset : one_chunk;
+    size_t n_max = 0;
+    for (int k = 0; k < K; k++) n_max = std::max(n_max, coff[k + 1] - coff[k]);
+    const size_t max_entries = n_max * (size_t)g.W;
     if (max_entries >= ((size_t)1 << 32)) { set_last_error("n * windows must be < 2^32"); return B200_ETOOLARGE; }
 
-    cudaEvent_t ev[7];
+    std::vector<cudaEvent_t> ev((size_t)K * 5 + 3);
     for (auto &e : ev) AB_CUDA(cudaEventCreate(&e));
     uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *sorted = nullptr, *block_totals = nullptr;
-    uint32_t *buckets = nullptr, *partials = nullptr, *window_sums = nullptr;
+    uint32_t *buckets = nullptr, *extra = nullptr, *partials = nullptr, *window_sums = nullptr;
     const size_t scan_blocks = (nb_total + kScanBlock - 1) / kScanBlock;
     AB_CUDA(cudaMallocAsync(&counts, nb_total * 4, st));
     AB_CUDA(cudaMallocAsync(&offsets, (nb_total + 1) * 4, st));
@@ -533,15 +564,16 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     AB_CUDA(cudaMallocAsync(&sorted, std::max<size_t>(max_entries, 1) * 4, st));
     AB_CUDA(cudaMallocAsync(&block_totals, scan_blocks * 4, st));
     AB_CUDA(cudaMallocAsync(&buckets, nb_total * 4 * L * 4, st));
+    if (K > 1) AB_CUDA(cudaMallocAsync(&extra, nb_total * 4 * L * 4, st));
     // accumulation tasks: T consecutive sorted entries per thread (>= ~128k tasks when the input allows it)
     uint32_t T = 512;
     while (T > 8 && max_entries / T < (1u << 17)) T >>= 1;
-    const uint32_t num_tasks = (uint32_t)((max_entries + T - 1) / T);
+    const uint32_t max_tasks = (uint32_t)((max_entries + T - 1) / T);
     uint32_t *head = nullptr, *tail = nullptr, *head_bucket = nullptr, *tail_bucket = nullptr;
-    AB_CUDA(cudaMallocAsync(&head, (size_t)std::max(num_tasks, 1u) * 4 * L * 4, st));
-    AB_CUDA(cudaMallocAsync(&tail, (size_t)std::max(num_tasks, 1u) * 4 * L * 4, st));
-    AB_CUDA(cudaMallocAsync(&head_bucket, (size_t)std::max(num_tasks, 1u) * 4, st));
-    AB_CUDA(cudaMallocAsync(&tail_bucket, (size_t)std::max(num_tasks, 1u) * 4, st));
+    AB_CUDA(cudaMallocAsync(&head, (size_t)std::max(max_tasks, 1u) * 4 * L * 4, st));
+    AB_CUDA(cudaMallocAsync(&tail, (size_t)std::max(max_tasks, 1u) * 4 * L * 4, st));
+    AB_CUDA(cudaMallocAsync(&head_bucket, (size_t)std::max(max_tasks, 1u) * 4, st));
+    AB_CUDA(cudaMallocAsync(&tail_bucket, (size_t)std::max(max_tasks, 1u) * 4, st));
     // reduction geometry: chunk of m = 2^log_m buckets per thread
     int log_m = 5;
     while (log_m > 0 && (g.nb >> log_m) < 64) log_m--;
@@ -550,67 +582,94 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     AB_CUDA(cudaMallocAsync(&partials, (size_t)g.W * chunks * 4 * L * 4, st));
     AB_CUDA(cudaMallocAsync(&window_sums, (size_t)g.W * 4 * L * 4, st));
 
-    AB_CUDA(cudaEventRecord(ev[0], st));
-    AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
-    const unsigned dblocks = (unsigned)((n + 255) / 256);
-    msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(d_scalars, n, g, 0, g.W, counts, nullptr);
-    AB_LAUNCHED();
-    AB_CUDA(cudaEventRecord(ev[1], st));
-    scan_block_totals_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals);
-    AB_LAUNCHED();
-    scan_totals_kernel<<<1, kScanThreads, 0, st>>>(block_totals, scan_blocks);
-    AB_LAUNCHED();
-    scan_apply_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals, offsets);
-    AB_LAUNCHED();
-    AB_CUDA(cudaMemcpyAsync(cursor, offsets, nb_total * 4, cudaMemcpyDeviceToDevice, st));
-    AB_CUDA(cudaEventRecord(ev[2], st));
-    // scatter in groups of windows so that the active write fronts (one 32-byte sector per bucket of the group) stay
-    // L2-resident: random 4-byte stores into a multi-GB array otherwise cost a DRAM sector each (measured 2.5x slower)
-    {
-        const size_t front_bytes = (size_t)g.nb * 32;
-        int group = (int)std::max<size_t>(1, ((size_t)48 << 20) / front_bytes);
-        for (int w0 = 0; w0 < g.W; w0 += group) {
-            msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(d_scalars, n, g, w0, std::min(g.W, w0 + group), cursor, sorted);
+    cudaEvent_t *e_begin = &ev[(size_t)K * 5], *e_acc_done = &ev[(size_t)K * 5 + 1], *e_end = &ev[(size_t)K * 5 + 2];
+    AB_CUDA(cudaEventRecord(*e_begin, st));
+    for (int k = 0; k < K; k++) {
+        const size_t nk = coff[k + 1] - coff[k];
+        cudaEvent_t *e = &ev[(size_t)k * 5];
+        if (ch.ready) AB_CUDA(cudaStreamWaitEvent(st, ch.ready[k], 0));
+        const uint32_t *scal = d_scalars + coff[k] * 8, *bas = d_bases + coff[k] * (2 * L);
+        uint32_t *target = k == 0 ? buckets : extra;
+        AB_CUDA(cudaEventRecord(e[0], st));
+        AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
+        const unsigned dblocks = (unsigned)((nk + 255) / 256);
+        if (nk) {
+            msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(scal, nk, g, 0, g.W, counts, nullptr);
             AB_LAUNCHED();
         }
+        AB_CUDA(cudaEventRecord(e[1], st));
+        scan_block_totals_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals);
+        AB_LAUNCHED();
+        scan_totals_kernel<<<1, kScanThreads, 0, st>>>(block_totals, scan_blocks);
+        AB_LAUNCHED();
+        scan_apply_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals, offsets);
+        AB_LAUNCHED();
+        AB_CUDA(cudaMemcpyAsync(cursor, offsets, nb_total * 4, cudaMemcpyDeviceToDevice, st));
+        AB_CUDA(cudaEventRecord(e[2], st));
+        // scatter in groups of windows so that the active write fronts (one 32-byte sector per bucket of the group) stay
+        // L2-resident: random 4-byte stores into a multi-GB array otherwise cost a DRAM sector each (measured 2.5x slower)
+        if (nk) {
+            const size_t front_bytes = (size_t)g.nb * 32;
+            int group = (int)std::max<size_t>(1, ((size_t)48 << 20) / front_bytes);
+            for (int w0 = 0; w0 < g.W; w0 += group) {
+                msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(scal, nk, g, w0, std::min(g.W, w0 + group), cursor, sorted);
+                AB_LAUNCHED();
+            }
+        }
+        AB_CUDA(cudaEventRecord(e[3], st));
+        AB_CUDA(cudaMemsetAsync(target, 0, nb_total * 4 * L * 4, st));
+        const uint32_t num_tasks = (uint32_t)((nk * (size_t)g.W + T - 1) / T);
+        if (num_tasks) {
+            msm_accumulate_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(bas, sorted, offsets, (uint32_t)nb_total, T, target, head, tail,
+                                                                            head_bucket, tail_bucket, num_tasks);
+            AB_LAUNCHED();
+            msm_fixup_small_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, target);
+            AB_LAUNCHED();
+            msm_fixup_big_kernel<C><<<num_tasks, 128, 128 * 4 * L * 4, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, target);
+            AB_LAUNCHED();
+        }
+        if (k > 0) {
+            msm_merge_kernel<C><<<(unsigned)((nb_total + 127) / 128), 128, 0, st>>>(buckets, extra, (uint32_t)nb_total);
+            AB_LAUNCHED();
+        }
+        AB_CUDA(cudaEventRecord(e[4], st));
     }
-    AB_CUDA(cudaEventRecord(ev[3], st));
-    AB_CUDA(cudaMemsetAsync(buckets, 0, nb_total * 4 * L * 4, st));
-    if (bases_ready) AB_CUDA(cudaStreamWaitEvent(st, bases_ready, 0));  // host path: bases still streaming in while we sorted
-    if (num_tasks) {
-        msm_accumulate_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, (uint32_t)nb_total, T, buckets, head, tail,
-                                                                        head_bucket, tail_bucket, num_tasks);
-        AB_LAUNCHED();
-        msm_fixup_small_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, buckets);
-        AB_LAUNCHED();
-        msm_fixup_big_kernel<C><<<num_tasks, 128, 128 * 4 * L * 4, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, buckets);
-        AB_LAUNCHED();
-    }
-    AB_CUDA(cudaEventRecord(ev[4], st));
+    AB_CUDA(cudaEventRecord(*e_acc_done, st));
     const unsigned rthreads = (unsigned)g.W * chunks;
     msm_bucket_reduce_kernel<C><<<(rthreads + 127) / 128, 128, 0, st>>>(buckets, g, log_m, chunks, partials);
     AB_LAUNCHED();
     msm_sum_partials_kernel<C><<<g.W, 128, 128 * 4 * L * 4, st>>>(partials, chunks, window_sums);
     AB_LAUNCHED();
-    AB_CUDA(cudaEventRecord(ev[5], st));
+    cudaEvent_t e_red;
+    AB_CUDA(cudaEventCreate(&e_red));
+    AB_CUDA(cudaEventRecord(e_red, st));
     msm_window_combine_kernel<C><<<1, 32, 0, st>>>(window_sums, g.W, g.c, d_out);
     AB_LAUNCHED();
-    AB_CUDA(cudaEventRecord(ev[6], st));
+    AB_CUDA(cudaEventRecord(*e_end, st));
 
-    uint32_t total_entries = 0;
-    AB_CUDA(cudaMemcpyAsync(&total_entries, offsets + nb_total, 4, cudaMemcpyDeviceToHost, st));
-    for (uint32_t *p : {counts, offsets, cursor, sorted, block_totals, buckets, partials, window_sums, head, tail, head_bucket, tail_bucket}) AB_CUDA(cudaFreeAsync(p, st));
+    for (uint32_t *p : {counts, offsets, cursor, sorted, block_totals, buckets, extra, partials, window_sums, head, tail, head_bucket, tail_bucket})
+        if (p) AB_CUDA(cudaFreeAsync(p, st));
     AB_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 6; i++) AB_CUDA(cudaEventElapsedTime(&t_last.ms[i], ev[i], ev[i + 1]));
-    AB_CUDA(cudaEventElapsedTime(&t_last.ms[6], ev[0], ev[6]));
+    for (int i = 0; i < 7; i++) t_last.ms[i] = 0.f;
+    for (int k = 0; k < K; k++)
+        for (int i = 0; i < 4; i++) {
+            float ms = 0.f;
+            AB_CUDA(cudaEventElapsedTime(&ms, ev[(size_t)k * 5 + i], ev[(size_t)k * 5 + i + 1]));
+            t_last.ms[i] += ms;  // digits+hist, scan, scatter, accumulate(+fixups, merge)
+        }
+    AB_CUDA(cudaEventElapsedTime(&t_last.ms[4], *e_acc_done, e_red));
+    AB_CUDA(cudaEventElapsedTime(&t_last.ms[5], e_red, *e_end));
+    AB_CUDA(cudaEventElapsedTime(&t_last.ms[6], *e_begin, *e_end));  // includes waiting for transfers on the host path
     for (auto &e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(e_red);
     t_last.c = g.c;
     t_last.W = g.W;
-    t_last.bucket_adds = total_entries;
+    t_last.bucket_adds = (unsigned long long)n * g.W;  // upper bound: zero digits are skipped
     return 0;
 }
 
-int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, cudaEvent_t bases_ready) {
+int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, int K, const size_t *chunk_off,
+                 const cudaEvent_t *ready) {
     if (!out_xyz_host || (n && (!d_bases || !d_scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
     const int L = curve == B200_CURVE_BLS12_381 ? 12 : 8;
@@ -622,10 +681,14 @@ int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n
         }
         return 0;
     }
+    MsmChunks ch;
+    ch.K = K;
+    ch.offset = chunk_off;
+    ch.ready = ready;
     uint32_t *d_out = nullptr;
     AB_CUDA(cudaMallocAsync(&d_out, 3 * L * 4, st));
-    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, bases_ready)
-                                           : msm_run<CurveBn>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, bases_ready);
+    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, ch)
+                                           : msm_run<CurveBn>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, ch);
     if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(out_xyz_host, d_out, 3 * L * 4, cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaFreeAsync(d_out, st));

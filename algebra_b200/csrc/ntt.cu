@@ -19,6 +19,7 @@
 // + (m-1) segment-twiddle multiplies.  2^24 = 256^3: 3*3.5 + 2 = 12.5 modmuls/element (136 IMAD.WIDE each).
 // HBM traffic: m reads + m writes of the data + (m-1) table reads (L2-resident except the pass-1 table).
 // 1/n of the inverse transform is folded into the pass-1 table; coset scaling is a separate element-wise kernel.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -375,11 +376,17 @@ template <class P> static int ntt_run(int field, uint4 *d_data, int log_n, bool 
         pp.has_scale = (plan.m == 1 && inverse) ? 1 : 0;
         for (int i = 0; i < 8; i++) pp.scale[i] = plan.scale[i];
         const int logB = log_seg - pp.r;
-        // G adjacent columns (non-last) / adjacent i1 rows (last) per block: 128-byte contiguous global accesses
-        int logG = 2;
+        // G adjacent columns per block.  Measured @2^24 (B200): G=1 4.09 ms, G=2 4.10 ms, G=4 4.59 ms, G=8 4.58 ms — small
+        // blocks (128-256 threads, 8-16 KB smem) keep ~10 blocks per SM so load/store phases of one block hide behind the
+        // butterflies of the others; G=2 keeps 64-byte contiguous runs.
+        int logG = 1;
+        if (const char *e = getenv("B200_NTT_LOGG")) logG = atoi(e);  // tuning knob
+        if (logG < 0) logG = 0;
+        if (logG > 3) logG = 3;
         if (!pp.is_last) { if (logG > logB) logG = logB; }
         else if (plan.m > 1) { if (logG > plan.radix_log[0]) logG = plan.radix_log[0]; }
         else logG = 0;
+        while (pp.r + logG - 1 > 9) logG--;  // at most 512 threads per block
         pp.logG = logG;
         const int tile = 1 << (pp.r + logG);
         const int threads = tile / 2 > 32 ? tile / 2 : 32;

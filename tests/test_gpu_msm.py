@@ -193,6 +193,9 @@ def test_config0_vs_reference_algorithm(cid, log_n):
     want = C.msm_affine(cid, bh, sh, threads=min(C.num_threads(), 32))
     got = ab.into_affine(cid, ab.msm(cid, d_bases, d_s))
     assert (got == want).all()
+    if log_n == 22:   # host-buffer entry point: 4-chunk H2D/compute pipeline with the bucket-merge kernel
+        got_host = ab.into_affine(cid, ab.msm(cid, from_dev(d_bases), sh))
+        assert (got_host == want).all()
     assert (want == expected_from_b(cid, from_dev(d_b), sh)).all()
 
 
@@ -215,6 +218,9 @@ def test_large_sizes_by_linear_identity(cid, log_n):
     want = cv.encode_affine([cv.mul(cv.G, tot % cv.fr.p)])[0]
     got = ab.into_affine(cid, ab.msm(cid, d_bases, d_s))
     assert (got == want).all()
+    if log_n == 22:   # host-buffer entry point: 4-chunk H2D/compute pipeline with the bucket-merge kernel
+        got_host = ab.into_affine(cid, ab.msm(cid, from_dev(d_bases), sh))
+        assert (got_host == want).all()
 
 
 @pytest.mark.parametrize("c", [0, 6, 11, 18])

@@ -46,6 +46,9 @@ def test_fp_ops(lib, fid, f):
         out = np.empty_like(A)
         assert lib.selftest_fp_op(fid, C.OPS[op], _p(A.view(np.uint32)), _p(B.view(np.uint32)), _p(out.view(np.uint32)), len(a)) == 0
         assert (out == want).all(), op
+    out = np.empty_like(A)   # symmetric squaring variant (op 9) == mul(a, a)
+    assert lib.selftest_fp_op(fid, 9, _p(A.view(np.uint32)), _p(A.view(np.uint32)), _p(out.view(np.uint32)), len(a)) == 0
+    assert (out == C.fp_op(fid, "sqr", A)).all()
     canon = np.ascontiguousarray(C.fp_op(fid, "into_bigint", A))
     out = np.empty_like(A)
     lib.selftest_fp_op(fid, 7, _p(canon.view(np.uint32)), _p(canon.view(np.uint32)), _p(out.view(np.uint32)), len(a))

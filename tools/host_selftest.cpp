@@ -21,6 +21,7 @@ template <class P> static int fp_op(int op, const uint32_t *a, const uint32_t *b
             case 6: F::from_mont(r, x); break;
             case 7: F::to_mont(r, x); break;
             case 8: F::inv(r, x); break;
+            case 9: F::sqr_sos(r, x); break;
             default: return 2;
         }
     }

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libalgebra_b200.so")
 
 EINVAL, ETOOLARGE, ENOMEM = -1, -2, -3
+SCALARS_FR_MONT, SCALARS_BIGINT, SCALARS_U8, SCALARS_U16, SCALARS_U32, SCALARS_U64 = range(6)
 
 # every symbol include/algebra_b200.h declares: name -> (restype, argtypes)
 _c = ctypes
@@ -21,6 +22,8 @@ SIGNATURES = {
     "b200_last_error": (_c.c_char_p, []),
     "b200_msm_sw_g1": (_c.c_int, [_c.c_int, _vp, _vp, _c.c_size_t, _vp]),
     "b200_msm_sw_g1_dev": (_c.c_int, [_c.c_int, _vp, _vp, _c.c_size_t, _vp, _vp]),
+    "b200_msm_sw_g1_scalars": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _c.c_size_t, _vp]),
+    "b200_msm_sw_g1_scalars_dev": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _c.c_size_t, _vp, _vp]),
     "b200_set_msm_window": (_c.c_int, [_c.c_int]),
     "b200_msm_window_for": (_c.c_int, [_c.c_int, _c.c_size_t]),
     "b200_g1_sum": (_c.c_int, [_c.c_int, _vp, _c.c_size_t, _vp]),
@@ -28,6 +31,9 @@ SIGNATURES = {
     "b200_ntt_fr": (_c.c_int, [_c.c_int, _vp, _c.c_uint32, _c.c_int, _vp]),
     "b200_ntt_fr_dev": (_c.c_int, [_c.c_int, _vp, _c.c_uint32, _c.c_int, _vp, _vp]),
     "b200_clear_cache": (_c.c_int, []),
+    "b200_poly_mul_size": (_c.c_size_t, [_c.c_int, _c.c_size_t, _c.c_size_t]),
+    "b200_poly_mul_fr": (_c.c_int, [_c.c_int, _vp, _c.c_size_t, _vp, _c.c_size_t, _vp]),
+    "b200_poly_mul_fr_dev": (_c.c_int, [_c.c_int, _vp, _c.c_size_t, _vp, _c.c_size_t, _vp, _vp]),
     "b200_gen_bases_dev": (_c.c_int, [_c.c_int, _c.c_uint64, _c.c_size_t, _vp, _vp, _vp]),
     "b200_gen_scalars_dev": (_c.c_int, [_c.c_int, _c.c_uint64, _c.c_size_t, _vp, _vp]),
     "b200_fp_op_dev": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _vp, _c.c_size_t, _c.c_int, _vp]),

@@ -60,16 +60,23 @@ static MsmGeom make_geom(int c, int scalar_bits) {
 // digits: canonical scalar -> signed digits (make_digits, :754-794); MODE 0 = histogram, 1 = scatter
 // ------------------------------------------------------------------------------------------------
 template <class C, int MODE>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restrict__ scalars, size_t n, MsmGeom g, int w_lo, int w_hi,
+__global__ void __launch_bounds__(256) msm_digits_kernel(const void *__restrict__ scalars_v, int kind, size_t n, MsmGeom g, int w_lo, int w_hi,
                                                          uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
     using FR = Fp<typename C::Fr>;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t s[8], k[10];
-    load_limbs_nc<8>(s, scalars + i * 8);
-    FR::from_mont(k, s);  // into_bigint (:60-62)
-    k[8] = 0;
-    k[9] = 0;
+    uint32_t k[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) k[j] = 0;
+    if (kind <= B200_SCALARS_BIGINT) {
+        uint32_t s[8];
+        load_limbs_nc<8>(s, (const uint32_t *)scalars_v + i * 8);
+        if (kind == B200_SCALARS_FR_MONT) FR::from_mont(k, s);  // into_bigint (:60-62)
+        else limbs_copy<8>(k, s);                               // msm_bigint: already canonical (:80-85)
+    } else if (kind == B200_SCALARS_U8) k[0] = ((const uint8_t *)scalars_v)[i];
+    else if (kind == B200_SCALARS_U16) k[0] = ((const uint16_t *)scalars_v)[i];
+    else if (kind == B200_SCALARS_U32) k[0] = ((const uint32_t *)scalars_v)[i];
+    else { uint2 v = ((const uint2 *)scalars_v)[i]; k[0] = v.x; k[1] = v.y; }
     const int c = g.c;
     const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
     uint32_t carry = 0;
@@ -78,8 +85,8 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint32_t *__restr
         uint64_t two = ((uint64_t)k[wi + 1] << 32) | k[wi];
         uint32_t coef = ((uint32_t)(two >> sh) & mask) + carry;
         uint32_t mag, neg = 0;
-        if (w == g.W - 1) {  // top digit stays unsigned (:789-791)
-            mag = coef;
+        if (w == g.W - 1) {  // top digit stays unsigned (:789-791); bits above the declared scalar width are ignored
+            mag = (((uint32_t)(two >> sh) & mask) & ((1u << g.top_bits) - 1)) + carry;
         } else {
             carry = (coef + half) >> c;
             if (carry) { mag = (1u << c) - coef; neg = 1; }  // digit = coef - 2^c in [-2^(c-1), 0)
@@ -532,18 +539,40 @@ __global__ void __launch_bounds__(128) msm_merge_kernel(uint32_t *__restrict__ b
 // soon as its `ready` event fires, so the host path overlaps the PCIe transfer of chunk k+1 with the arithmetic of chunk k;
 // chunk 0 accumulates straight into `buckets`, later chunks into a second array that is merged bucket-wise.  The bucket
 // reduction and window combine run once at the end.
+static int scalar_kind_bits(int kind, int field_bits) {
+    switch (kind) {
+        case B200_SCALARS_U8: return 8;
+        case B200_SCALARS_U16: return 16;
+        case B200_SCALARS_U32: return 32;
+        case B200_SCALARS_U64: return 64;
+        default: return field_bits;  // Fr::MODULUS_BIT_SIZE (variable_base/mod.rs:451)
+    }
+}
+size_t scalar_kind_bytes(int kind) {
+    switch (kind) {
+        case B200_SCALARS_U8: return 1;
+        case B200_SCALARS_U16: return 2;
+        case B200_SCALARS_U32: return 4;
+        case B200_SCALARS_U64: return 8;
+        default: return 32;
+    }
+}
+
 struct MsmChunks {
     int K = 1;
     const size_t *offset = nullptr;      // K+1 element offsets into bases / scalars
     const cudaEvent_t *ready = nullptr;  // K events (or nullptr: data already resident)
 };
 
-template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d_scalars, size_t n, uint32_t *d_out, cudaStream_t st,
+template <class C> static int msm_run(const uint32_t *d_bases, const void *d_scalars, int kind, size_t n, uint32_t *d_out, cudaStream_t st,
                                       const MsmChunks &ch) {
     constexpr int L = C::Fq::L;
     if (n >= ((size_t)1 << 31)) { set_last_error("n must be < 2^31"); return B200_ETOOLARGE; }
-    const int c = t_window_override ? t_window_override : msm_auto_window(n, C::SCALAR_BITS);
-    const MsmGeom g = make_geom(c, C::SCALAR_BITS);
+    const int scalar_bits = scalar_kind_bits(kind, C::SCALAR_BITS);
+    const size_t scalar_bytes = scalar_kind_bytes(kind);
+    int c = t_window_override ? t_window_override : msm_auto_window(n, scalar_bits);
+    if (c > scalar_bits) c = scalar_bits;
+    const MsmGeom g = make_geom(c, scalar_bits);
     const size_t nb_total = g.total_buckets;
     const size_t one_chunk[2] = {0, n};
     const int K = ch.K > 1 ? ch.K : 1;
@@ -588,13 +617,14 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
         const size_t nk = coff[k + 1] - coff[k];
         cudaEvent_t *e = &ev[(size_t)k * 5];
         if (ch.ready) AB_CUDA(cudaStreamWaitEvent(st, ch.ready[k], 0));
-        const uint32_t *scal = d_scalars + coff[k] * 8, *bas = d_bases + coff[k] * (2 * L);
+        const void *scal = (const char *)d_scalars + coff[k] * scalar_bytes;
+        const uint32_t *bas = d_bases + coff[k] * (2 * L);
         uint32_t *target = k == 0 ? buckets : extra;
         AB_CUDA(cudaEventRecord(e[0], st));
         AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
         const unsigned dblocks = (unsigned)((nk + 255) / 256);
         if (nk) {
-            msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(scal, nk, g, 0, g.W, counts, nullptr);
+            msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(scal, kind, nk, g, 0, g.W, counts, nullptr);
             AB_LAUNCHED();
         }
         AB_CUDA(cudaEventRecord(e[1], st));
@@ -612,7 +642,7 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
             const size_t front_bytes = (size_t)g.nb * 32;
             int group = (int)std::max<size_t>(1, ((size_t)48 << 20) / front_bytes);
             for (int w0 = 0; w0 < g.W; w0 += group) {
-                msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(scal, nk, g, w0, std::min(g.W, w0 + group), cursor, sorted);
+                msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(scal, kind, nk, g, w0, std::min(g.W, w0 + group), cursor, sorted);
                 AB_LAUNCHED();
             }
         }
@@ -668,8 +698,9 @@ template <class C> static int msm_run(const uint32_t *d_bases, const uint32_t *d
     return 0;
 }
 
-int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, int K, const size_t *chunk_off,
-                 const cudaEvent_t *ready) {
+int msm_dispatch(int curve, int kind, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz_host, cudaStream_t st, int K,
+                 const size_t *chunk_off, const cudaEvent_t *ready) {
+    if (kind < B200_SCALARS_FR_MONT || kind > B200_SCALARS_U64) { set_last_error("unknown scalar kind"); return B200_EINVAL; }
     if (!out_xyz_host || (n && (!d_bases || !d_scalars))) { set_last_error("null pointer"); return B200_EINVAL; }
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) { set_last_error("unknown curve id"); return B200_EINVAL; }
     const int L = curve == B200_CURVE_BLS12_381 ? 12 : 8;
@@ -687,8 +718,8 @@ int msm_dispatch(int curve, const void *d_bases, const void *d_scalars, size_t n
     ch.ready = ready;
     uint32_t *d_out = nullptr;
     AB_CUDA(cudaMallocAsync(&d_out, 3 * L * 4, st));
-    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, ch)
-                                           : msm_run<CurveBn>((const uint32_t *)d_bases, (const uint32_t *)d_scalars, n, d_out, st, ch);
+    int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, d_scalars, kind, n, d_out, st, ch)
+                                           : msm_run<CurveBn>((const uint32_t *)d_bases, d_scalars, kind, n, d_out, st, ch);
     if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(out_xyz_host, d_out, 3 * L * 4, cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaFreeAsync(d_out, st));

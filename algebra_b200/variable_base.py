@@ -35,10 +35,15 @@ def _rows(x, width: int) -> int:
     return np.asarray(x).size // width
 
 
-def msm_unchecked(curve: G1Curve | int, bases, scalars) -> np.ndarray:
+_KIND_DTYPE = {_lib.SCALARS_FR_MONT: (np.uint64, 4), _lib.SCALARS_BIGINT: (np.uint64, 4), _lib.SCALARS_U8: (np.uint8, 1),
+               _lib.SCALARS_U16: (np.uint16, 1), _lib.SCALARS_U32: (np.uint32, 1), _lib.SCALARS_U64: (np.uint64, 1)}
+
+
+def _msm_kind(curve: G1Curve | int, kind: int, bases, scalars) -> np.ndarray:
     cv = CURVES[curve] if isinstance(curve, int) else curve
     N = cv.N
-    n = min(_rows(bases, 2 * N), _rows(scalars, 4))
+    dtype, width = _KIND_DTYPE[kind]
+    n = min(_rows(bases, 2 * N), _rows(scalars, width))
     out = np.zeros(3 * N, dtype=np.uint64)
     outp = out.ctypes.data_as(ctypes.c_void_p)
     if _is_torch(bases) != _is_torch(scalars):
@@ -47,16 +52,86 @@ def msm_unchecked(curve: G1Curve | int, bases, scalars) -> np.ndarray:
         import torch
         if not (bases.is_cuda and scalars.is_cuda and bases.is_contiguous() and scalars.is_contiguous()):
             raise TypeError("device path needs contiguous CUDA tensors")
-        assert bases.element_size() == 8 and scalars.element_size() == 8
+        assert bases.element_size() == 8 and scalars.element_size() == np.dtype(dtype).itemsize
         with torch.cuda.device(bases.device):
             st = torch.cuda.current_stream().cuda_stream
-            _lib.check(_lib.lib().b200_msm_sw_g1_dev(cv.cid, bases.data_ptr(), scalars.data_ptr(), n, outp, st))
+            _lib.check(_lib.lib().b200_msm_sw_g1_scalars_dev(cv.cid, kind, bases.data_ptr(), scalars.data_ptr(), n, outp, st))
     else:
-        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * N)[:n]
-        s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)[:n]
-        b, s = np.ascontiguousarray(b), np.ascontiguousarray(s)
-        _lib.check(_lib.lib().b200_msm_sw_g1(cv.cid, b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), n, outp))
+        b = np.ascontiguousarray(np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * N)[:n])
+        s = np.ascontiguousarray(np.ascontiguousarray(scalars, dtype=dtype).reshape(-1, width)[:n])
+        _lib.check(_lib.lib().b200_msm_sw_g1_scalars(cv.cid, kind, b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), n, outp))
     return out
+
+
+def msm_unchecked(curve: G1Curve | int, bases, scalars) -> np.ndarray:
+    return _msm_kind(curve, _lib.SCALARS_FR_MONT, bases, scalars)
+
+
+def msm_bigint(curve: G1Curve | int, bases, bigints) -> np.ndarray:
+    """VariableBaseMSM::msm_bigint (:80-85): scalars are canonical `BigInt<4>` limbs ((n, 4) uint64, not Montgomery)."""
+    return _msm_kind(curve, _lib.SCALARS_BIGINT, bases, bigints)
+
+
+def msm_u1(curve, bases, scalars) -> np.ndarray:
+    """msm_u1 (:89-91): boolean scalars (one byte each, like Rust's `&[bool]`)."""
+    s = scalars if _is_torch(scalars) else np.ascontiguousarray(scalars).astype(np.uint8)
+    return _msm_kind(curve, _lib.SCALARS_U8, bases, s)
+
+
+def msm_u8(curve, bases, scalars) -> np.ndarray:
+    return _msm_kind(curve, _lib.SCALARS_U8, bases, scalars)
+
+
+def msm_u16(curve, bases, scalars) -> np.ndarray:
+    return _msm_kind(curve, _lib.SCALARS_U16, bases, scalars)
+
+
+def msm_u32(curve, bases, scalars) -> np.ndarray:
+    return _msm_kind(curve, _lib.SCALARS_U32, bases, scalars)
+
+
+def msm_u64(curve, bases, scalars) -> np.ndarray:
+    return _msm_kind(curve, _lib.SCALARS_U64, bases, scalars)
+
+
+def msm_chunks(curve: G1Curve | int, bases_stream, scalars_stream, step: int = 1 << 20) -> np.ndarray:
+    """VariableBaseMSM::msm_chunks (:119-150): the scalar stream may be shorter than the base stream; the LAST
+    len(scalars) bases are used (`skip(bases.len() - scalars.len())`), folded `step` pairs at a time."""
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    nb, ns = _rows(bases_stream, 2 * cv.N), _rows(scalars_stream, 4)
+    assert ns <= nb, "scalars_stream.len() <= bases_stream.len()"
+    b = bases_stream.reshape(-1, 2 * cv.N)[nb - ns:]
+    s = scalars_stream.reshape(-1, 4)
+    parts = [msm_unchecked(cv, b[lo:lo + step], s[lo:lo + step]) for lo in range(0, ns, step)]
+    if not parts:
+        return msm_unchecked(cv, b[:0], s[:0])
+    return parts[0] if len(parts) == 1 else sum_points(cv, np.stack(parts))
+
+
+class ChunkedPippenger:
+    """stream_pippenger.rs:10-66: buffer (base, bigint scalar) pairs, flush through msm_bigint every `buf_size`."""
+
+    def __init__(self, curve: G1Curve | int, max_msm_buffer: int):
+        self.cv = CURVES[curve] if isinstance(curve, int) else curve
+        self.buf_size = max_msm_buffer
+        self.bases, self.scalars, self.results = [], [], []
+
+    def add(self, base, scalar_bigint):
+        self.bases.append(np.asarray(base, dtype=np.uint64).reshape(2 * self.cv.N))
+        self.scalars.append(np.asarray(scalar_bigint, dtype=np.uint64).reshape(4))
+        if len(self.scalars) == self.buf_size:
+            self._flush()
+
+    def _flush(self):
+        self.results.append(msm_bigint(self.cv, np.stack(self.bases), np.stack(self.scalars)))
+        self.bases, self.scalars = [], []
+
+    def finalize(self) -> np.ndarray:
+        if self.scalars:
+            self._flush()
+        if not self.results:
+            return msm_unchecked(self.cv, np.zeros((0, 2 * self.cv.N), np.uint64), np.zeros((0, 4), np.uint64))
+        return sum_points(self.cv, np.stack(self.results))
 
 
 def msm(curve: G1Curve | int, bases, scalars) -> np.ndarray:

@@ -60,6 +60,20 @@ int b200_msm_sw_g1(int curve, const uint64_t *bases, const uint64_t *scalars, si
 int b200_msm_sw_g1_dev(int curve, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz,
                        void *stream);
 
+/* The rest of the VariableBaseMSM surface (ec/src/scalar_mul/variable_base/mod.rs:80-115), which the reference does NOT route
+ * through the SWCurveConfig::msm hook: scalars given as canonical BigInt<4> (`msm_bigint`) or as small unsigned integers
+ * (`msm_u1` = bool bytes use U8, `msm_u8`, `msm_u16`, `msm_u32`, `msm_u64`).  Small kinds use ceil(bits/c) windows only.
+ *   scalars: n elements of 32 B (FR_MONT, BIGINT) or 1/2/4/8 B (U8..U64)                                                  */
+#define B200_SCALARS_FR_MONT 0
+#define B200_SCALARS_BIGINT 1
+#define B200_SCALARS_U8 2
+#define B200_SCALARS_U16 3
+#define B200_SCALARS_U32 4
+#define B200_SCALARS_U64 5
+int b200_msm_sw_g1_scalars(int curve, int scalar_kind, const uint64_t *bases, const void *scalars, size_t n, uint64_t *out_xyz);
+int b200_msm_sw_g1_scalars_dev(int curve, int scalar_kind, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz,
+                               void *stream);
+
 /* Pippenger window size c used by subsequent MSM calls on this thread's device: 0 = automatic.
  * (The reference's rule is ln_without_floats(n)+2, ec/src/scalar_mul/variable_base/mod.rs:445-449; any c
  * yields the same group element.)  b200_msm_window_for(n) reports what "automatic" picks. */
@@ -85,6 +99,15 @@ int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const ui
 /* device-resident variant: d_data is a device pointer; coset_offset stays a host pointer. */
 int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset_offset,
                     void *stream);
+/* Dense polynomial product over the scalar field, device-resident end to end: the body of
+ * `impl Mul<&DensePolynomial<F>> for &DensePolynomial<F>` (poly/src/polynomial/univariate/dense.rs:641-656) —
+ * domain of size n = next_pow2(la + lb - 1), fft(a), fft(b), `self_evals *= &other_evals`
+ * (poly/src/evaluations/univariate/mod.rs), interpolate (ifft) — with the three vectors staying in HBM between the steps.
+ *   a, b   la / lb coefficients (x 4 u64, Montgomery), la, lb >= 1      out   n x 4 u64 (the caller trims leading zeros
+ *   like DensePolynomial::from_coefficients_vec); b200_poly_mul_size gives n (0 if past TWO_ADICITY).              */
+size_t b200_poly_mul_size(int field, size_t la, size_t lb);
+int b200_poly_mul_fr(int field, const uint64_t *a, size_t la, const uint64_t *b, size_t lb, uint64_t *out);
+int b200_poly_mul_fr_dev(int field, const void *d_a, size_t la, const void *d_b, size_t lb, void *d_out, void *stream);
 /* drop cached twiddle tables / scratch of the current device */
 int b200_clear_cache(void);
 

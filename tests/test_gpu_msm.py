@@ -248,3 +248,41 @@ def test_heavy_buckets_and_short_top_window(c):
         assert (ab.into_affine(cid, ab.msm(cid, d_bases, to_dev(sh))) == want).all()
     finally:
         M.set_window(0)
+
+
+def test_msm_bigint_and_small_scalar_entry_points():
+    """msm_bigint / msm_u1 / msm_u8..u64 (variable_base/mod.rs:80-115; test_var_base_msm_specialized, msm.rs:74-110),
+    msm_chunks (:119-150) and ChunkedPippenger (stream_pippenger.rs) — checked by MSM(b_i*G, s_i) = (sum s_i b_i)*G."""
+    cid, n = 0, 3000
+    cv, fr = O.BLS12_381, O.BLS12_381_FR
+    d_bases, d_b, d_s = synth(cid, n, 9001)
+    bh, bb = from_dev(d_bases), [int(x) for x in from_dev(d_b)]
+    rng = np.random.default_rng(3)
+
+    def want(sc):
+        return cv.encode_affine([cv.mul(cv.G, sum(b * int(s) for b, s in zip(bb, sc)) % fr.p)])[0]
+
+    for bits, fn, dt in ((8, ab.msm_u8, np.uint8), (16, ab.msm_u16, np.uint16), (32, ab.msm_u32, np.uint32), (64, ab.msm_u64, np.uint64)):
+        sc = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(dt)
+        sc[:3] = (0, 1, (1 << bits) - 1)
+        w = want(sc)
+        assert (ab.into_affine(cid, fn(cid, bh, sc)) == w).all(), bits                       # host path
+        import torch
+        dsc = torch.from_numpy(sc.view({1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[sc.itemsize])).cuda()
+        assert (ab.into_affine(cid, fn(cid, d_bases, dsc)) == w).all(), bits                   # device path
+    bools = rng.integers(0, 2, size=n).astype(bool)
+    assert (ab.into_affine(cid, ab.msm_u1(cid, bh, bools)) == want(bools.astype(np.uint64))).all()
+    # msm_bigint: canonical limbs
+    sh = from_dev(d_s)
+    canon = C.fp_op(1, "into_bigint", sh)
+    w = ab.into_affine(cid, ab.msm(cid, bh, sh))
+    assert (ab.into_affine(cid, ab.msm_bigint(cid, bh, canon)) == w).all()
+    # msm_chunks: scalar stream shorter than the base stream -> the LAST len(scalars) bases are used
+    k = 1000
+    got = ab.into_affine(cid, ab.msm_chunks(cid, bh, sh[:k], step=256))
+    assert (got == ab.into_affine(cid, ab.msm(cid, bh[n - k:], sh[:k]))).all()
+    # ChunkedPippenger
+    cp = ab.ChunkedPippenger(cid, 128)
+    for i in range(300):
+        cp.add(bh[i], canon[i])
+    assert (ab.into_affine(cid, cp.finalize()) == ab.into_affine(cid, ab.msm(cid, bh[:300], sh[:300]))).all()

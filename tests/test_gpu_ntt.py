@@ -125,3 +125,28 @@ def test_full_size_properties(log_n):
     fxs = dom.fft(xs)
     rows = np.random.default_rng(1).integers(0, n, size=4096)
     assert (fxs[rows] == C.fp_op(ofid, "add", np.ascontiguousarray(fx[rows]), np.ascontiguousarray(fs[rows]))).all()
+
+
+def test_poly_mul_and_interpolate():
+    """DensePolynomial * DensePolynomial (dense.rs:641-656) vs schoolbook multiplication with Python ints, host and
+    device-resident paths; Evaluations::interpolate = ifft + trimming."""
+    fr, _ = FR[0]
+    rnd = random.Random(12)
+    for la, lb in ((1, 1), (3, 5), (64, 65), (300, 17), (1000, 1000)):
+        a = [rnd.randrange(fr.p) for _ in range(la)]
+        b = [rnd.randrange(fr.p) for _ in range(lb)]
+        b[-1] = b[-1] or 1
+        a[-1] = a[-1] or 1
+        want = [0] * (la + lb - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b):
+                want[i + j] = (want[i + j] + x * y) % fr.p
+        A, B = fr.encode(a), fr.encode(b)
+        got = ab.poly_mul(0, A, B)
+        assert fr.decode(got) == want
+        gd = from_dev(ab.poly_mul(0, to_dev(A), to_dev(B)))
+        assert fr.decode(gd[: la + lb - 1]) == want and not gd[la + lb - 1:].any()
+    assert ab.poly_mul(0, np.zeros((0, 4), np.uint64), fr.encode([1, 2])).shape == (0, 4)
+    dom = ab.Radix2EvaluationDomain.new(0, 64)
+    coeffs = fr.encode([rnd.randrange(fr.p) for _ in range(40)])
+    assert (ab.interpolate(dom, dom.fft(coeffs)) == coeffs).all()

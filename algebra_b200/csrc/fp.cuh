@@ -132,6 +132,12 @@ AB_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
 
 #include "field_consts.inc"
 
+// Same fields, but Fp::mul keeps its row pairs in a real loop instead of unrolling all L rows: ~3x less code per multiplication,
+// so a 10-multiplication point addition fits the instruction cache (the fully unrolled madd body is ~53 KB of SASS and ncu shows
+// `no_instruction` stalls on it).  Used by the MSM accumulation kernel only.
+struct BlsFqRolled : BlsFq { static constexpr bool ROLLED = true; };
+struct BnFqRolled : BnFq { static constexpr bool ROLLED = true; };
+
 // ------------------------------------------------------------------------------------------------
 // Generic helpers on raw limb arrays
 // ------------------------------------------------------------------------------------------------
@@ -272,10 +278,20 @@ template <class P> struct Fp {
         uint32_t ev[L], od[L];
         mont_row<true>(ev, od, a, b[0]);
         mont_row<false>(od, ev, a, b[1]);
+        if (P::ROLLED) {
+            uint32_t bb[L];  // dynamically indexed below -> lives in (L1-resident) local memory
+            limbs_copy<L>(bb, b);
+#pragma unroll 1
+            for (int i = 2; i < L; i += 2) {
+                mont_row<false>(ev, od, a, bb[i]);
+                mont_row<false>(od, ev, a, bb[i + 1]);
+            }
+        } else {
 #pragma unroll
-        for (int i = 2; i < L; i += 2) {
-            mont_row<false>(ev, od, a, b[i]);
-            mont_row<false>(od, ev, a, b[i + 1]);
+            for (int i = 2; i < L; i += 2) {
+                mont_row<false>(ev, od, a, b[i]);
+                mont_row<false>(od, ev, a, b[i + 1]);
+            }
         }
         // after an even number of rows: T = (od>>32) + ev
         uint32_t t[L];

@@ -29,11 +29,15 @@ namespace ab200 {
 
 struct CurveBls {
     using Fq = BlsFq;
+    // Hot-loop field type.  BlsFqRolled (row pairs in a real loop, 4.6k instead of 7.6k SASS instructions) was measured
+    // SLOWER on B200 (accumulate 338 -> 371 ms @2^26): the unrolled rows let ptxas interleave six carry chains.
+    using FqAcc = BlsFq;
     using Fr = BlsFr;
     static constexpr int SCALAR_BITS = 255;  // Fr::MODULUS_BIT_SIZE (variable_base/mod.rs:451)
 };
 struct CurveBn {
     using Fq = BnFq;
+    using FqAcc = BnFq;
     using Fr = BnFr;
     static constexpr int SCALAR_BITS = 254;
 };
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__r
                                                              uint32_t *__restrict__ buckets, uint32_t *__restrict__ head,
                                                              uint32_t *__restrict__ tail, uint32_t *__restrict__ head_bucket,
                                                              uint32_t *__restrict__ tail_bucket, uint32_t num_tasks) {
-    using P = typename C::Fq;
+    using P = typename C::FqAcc;
     using E = Ec<P>;
     constexpr int L = P::L;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -716,6 +720,15 @@ int msm_dispatch(int curve, int kind, const void *d_bases, const void *d_scalars
     ch.K = K;
     ch.offset = chunk_off;
     ch.ready = ready;
+    // device-resident inputs too large for one 32-bit entry index space (n * windows >= 2^32): split into equal chunks
+    std::vector<size_t> auto_off;
+    if (K <= 1 && n > ((size_t)1 << 27)) {
+        const int kk = (int)((n + ((size_t)1 << 27) - 1) >> 27);
+        for (int k = 0; k <= kk; k++) auto_off.push_back(n * (size_t)k / kk);
+        ch.K = kk;
+        ch.offset = auto_off.data();
+        ch.ready = nullptr;
+    }
     uint32_t *d_out = nullptr;
     AB_CUDA(cudaMallocAsync(&d_out, 3 * L * 4, st));
     int rc = curve == B200_CURVE_BLS12_381 ? msm_run<CurveBls>((const uint32_t *)d_bases, d_scalars, kind, n, d_out, st, ch)

@@ -150,3 +150,27 @@ def test_poly_mul_and_interpolate():
     dom = ab.Radix2EvaluationDomain.new(0, 64)
     coeffs = fr.encode([rnd.randrange(fr.p) for _ in range(40)])
     assert (ab.interpolate(dom, dom.fft(coeffs)) == coeffs).all()
+
+
+def test_four_pass_plan_2e25():
+    """log n = 25 needs four passes (7+6+6+6): exercises the multi-digit reversal of the last pass.  Checked by the
+    closed form of a sparse input and by the round trip."""
+    import torch
+    fr, _ = FR[0]
+    log_n = 25
+    n = 1 << log_n
+    dom = ab.Radix2EvaluationDomain.new(0, n)
+    idx = [1, 12345, n // 2 + 77, n - 3]
+    vals = [3, fr.p - 2, 0x123456789, 7]
+    t = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    enc = fr.encode(vals)
+    for i, e in zip(idx, enc):
+        t[i] = torch.from_numpy(e.view(np.int64)).cuda()
+    x0 = t.clone()
+    dom.fft_in_place(t)
+    g = O.Radix2Domain(fr, n).group_gen
+    for i in [0, 1, 5, n // 2, n - 1, 0x155555 % n, (n // 3) | 1, 1 << 19, (1 << 19) + (1 << 7) + 1]:
+        want = sum(v * pow(g, j * i, fr.p) for j, v in zip(idx, vals)) % fr.p
+        assert fr.decode(t[i].cpu().numpy().view(np.uint64))[0] == want, i
+    dom.ifft_in_place(t)
+    assert torch.equal(t, x0)

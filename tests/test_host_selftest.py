@@ -49,6 +49,10 @@ def test_fp_ops(lib, fid, f):
     out = np.empty_like(A)   # symmetric squaring variant (op 9) == mul(a, a)
     assert lib.selftest_fp_op(fid, 9, _p(A.view(np.uint32)), _p(A.view(np.uint32)), _p(out.view(np.uint32)), len(a)) == 0
     assert (out == C.fp_op(fid, "sqr", A)).all()
+    if fid in (0, 2):        # rolled-row multiplication variant (BlsFqRolled / BnFqRolled) == the unrolled one
+        out = np.empty_like(A)
+        assert lib.selftest_fp_op({0: 4, 2: 5}[fid], 0, _p(A.view(np.uint32)), _p(B.view(np.uint32)), _p(out.view(np.uint32)), len(a)) == 0
+        assert (out == C.fp_op(fid, "mul", A, B)).all()
     canon = np.ascontiguousarray(C.fp_op(fid, "into_bigint", A))
     out = np.empty_like(A)
     lib.selftest_fp_op(fid, 7, _p(canon.view(np.uint32)), _p(canon.view(np.uint32)), _p(out.view(np.uint32)), len(a))

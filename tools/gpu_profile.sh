@@ -6,7 +6,7 @@ R=${1:-r01}
 mkdir -p gpurun_out
 free -g | head -2 > gpurun_out/${R}_host.txt; nproc >> gpurun_out/${R}_host.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.log 2>&1
-python bench.py --steps ${STEPS:-3} --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
+python bench.py --steps ${STEPS:-5} --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 tail -c 3000 gpurun_out/${R}_bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-verify > gpurun_out/${R}_ncu_bench.log 2>&1

@@ -47,6 +47,8 @@ template <class P> static int ec_op(int op, const uint32_t *a, const uint32_t *b
 }
 extern "C" int selftest_fp_op(int field, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
     switch (field) {
+        case 4: return fp_op<BlsFqRolled>(op, a, b, out, n);   // rolled-row variants used by the MSM accumulation kernel
+        case 5: return fp_op<BnFqRolled>(op, a, b, out, n);
         case 0: return fp_op<BlsFq>(op, a, b, out, n);
         case 1: return fp_op<BlsFr>(op, a, b, out, n);
         case 2: return fp_op<BnFq>(op, a, b, out, n);

@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200_poly_mul_fr_dev": (_c.c_int, [_c.c_int, _vp, _c.c_size_t, _vp, _c.c_size_t, _vp, _vp]),
     "b200_gen_bases_dev": (_c.c_int, [_c.c_int, _c.c_uint64, _c.c_size_t, _vp, _vp, _vp]),
     "b200_gen_scalars_dev": (_c.c_int, [_c.c_int, _c.c_uint64, _c.c_size_t, _vp, _vp]),
+    "b200_g1_batch_mul_dev": (_c.c_int, [_c.c_int, _vp, _vp, _c.c_size_t, _vp, _vp]),
+    "b200_g1_normalize_batch_dev": (_c.c_int, [_c.c_int, _vp, _c.c_size_t, _vp, _vp]),
     "b200_fp_op_dev": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _vp, _c.c_size_t, _c.c_int, _vp]),
     "b200_ec_op_dev": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _vp, _c.c_size_t, _vp]),
     "b200_msm_last_timings": (_c.c_int, [_c.POINTER(_c.c_float), _c.POINTER(_c.c_int), _c.POINTER(_c.c_int),

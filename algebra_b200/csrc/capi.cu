@@ -16,6 +16,8 @@ int fp_op_dispatch(int field, int op, const void *a, const void *b, void *out, s
 int ec_op_dispatch(int curve, int op, const void *a, const void *b, void *out, size_t n, cudaStream_t st);
 int gen_bases_dispatch(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, cudaStream_t st);
 int gen_scalars_dispatch(int field, uint64_t seed, size_t n, void *d_scalars, cudaStream_t st);
+int batch_mul_dispatch(int curve, const uint64_t *base_xy, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+int normalize_batch_dispatch(int curve, const void *d_xyz, size_t n, void *d_out, cudaStream_t st);
 }  // namespace ab200
 using namespace ab200;
 
@@ -196,6 +198,20 @@ int b200_gen_bases_dev(int curve, uint64_t seed, size_t n, void *d_bases, void *
 int b200_gen_scalars_dev(int field, uint64_t seed, size_t n, void *d_scalars, void *stream) {
     { int irc = ensure_device_init(); if (irc) return irc; }
     int rc = gen_scalars_dispatch(field, seed, n, d_scalars, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int b200_g1_batch_mul_dev(int curve, const uint64_t *base_xy, const void *d_scalars, size_t n, void *d_out_xy, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
+    int rc = batch_mul_dispatch(curve, base_xy, d_scalars, n, d_out_xy, (cudaStream_t)stream);
+    if (rc) return rc;
+    AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int b200_g1_normalize_batch_dev(int curve, const void *d_xyz, size_t n, void *d_out_xy, void *stream) {
+    { int irc = ensure_device_init(); if (irc) return irc; }
+    int rc = normalize_batch_dispatch(curve, d_xyz, n, d_out_xy, (cudaStream_t)stream);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;

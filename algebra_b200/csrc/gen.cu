@@ -11,6 +11,8 @@
 
 namespace ab200 {
 
+static constexpr int kGenBatch = 8;  // points normalised with one inversion per thread
+
 __host__ __device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t idx) {
     uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -64,7 +66,6 @@ template <class P> __global__ void gen_table_kernel(uint32_t *table) {
     (void)sizeof(F);
 }
 
-static constexpr int kGenBatch = 8;
 template <class P> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64_t seed, size_t n, const uint32_t *__restrict__ table,
                                                                          uint32_t *__restrict__ bases, uint64_t *__restrict__ bvals) {
     using E = Ec<P>;
@@ -109,6 +110,116 @@ template <class P> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64
     }
 }
 
+// ---- fixed-base batch multiplication and batch normalisation as public operations ----------------
+// table[w*256 + d] = (d * 256^w) * B for an arbitrary affine base B, w < windows  (BatchMulPreprocessing::new,
+// ec/src/scalar_mul/mod.rs:163-215, with an 8-bit window)
+template <class P> __global__ void batch_table_kernel(LimbArg<P::L> bx, LimbArg<P::L> by, int windows, uint32_t *table) {
+    using E = Ec<P>;
+    constexpr int L = P::L;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= windows * 256) return;
+    int w = t >> 8, d = t & 255;
+    typename E::J base, acc;
+    E::jac_set_zero(base);
+    if (!E::affine_is_zero(bx.v, by.v)) {
+#pragma unroll
+        for (int i = 0; i < L; i++) { base.x[i] = bx.v[i]; base.y[i] = by.v[i]; base.z[i] = P::ONE(i); }
+    }
+    for (int k = 0; k < 8 * w; k++) E::jac_dbl(base);
+    E::jac_set_zero(acc);
+    for (int bit = 7; bit >= 0; bit--) {
+        E::jac_dbl(acc);
+        if ((d >> bit) & 1) E::jac_add(acc, base);
+    }
+    uint32_t ax[L], ay[L];
+    E::jac_to_affine(ax, ay, acc);
+    store_limbs<L>(table + (size_t)t * 2 * L, ax);
+    store_limbs<L>(table + (size_t)t * 2 * L + L, ay);
+}
+
+// XYZZ points of one thread -> affine with ONE inversion (Montgomery's trick, ff/src/fields/mod.rs:358-420); identity -> (0,0)
+template <class P, int B> __device__ __forceinline__ void xyzz_batch_to_affine(Xyzz<P> *pts, int cnt, uint32_t *out /* cnt x 2L */) {
+    using E = Ec<P>;
+    using F = Fp<P>;
+    constexpr int L = P::L;
+    uint32_t prefix[B][L], run[L];
+    F::set_one(run);
+    for (int k = 0; k < cnt; k++) {
+        limbs_copy<L>(prefix[k], run);                        // product of the non-identity zzz before k
+        if (!E::xyzz_is_zero(pts[k])) F::mul(run, run, pts[k].zzz);
+    }
+    uint32_t inv[L];
+    F::inv(inv, run);
+    for (int k = cnt - 1; k >= 0; k--) {
+        uint32_t ax[L], ay[L];
+        if (E::xyzz_is_zero(pts[k])) {
+            F::set_zero(ax);
+            F::set_zero(ay);
+        } else {
+            uint32_t zi[L], t[L];
+            F::mul(zi, inv, prefix[k]);                        // 1/zzz_k
+            F::mul(inv, inv, pts[k].zzz);
+            F::mul(t, pts[k].zz, zi);                          // zz/zzz = 1/z ; (1/z)^2 = 1/zz
+            F::sqr(t, t);
+            F::mul(ax, pts[k].x, t);
+            F::mul(ay, pts[k].y, zi);
+        }
+        store_limbs<L>(out + (size_t)k * 2 * L, ax);
+        store_limbs<L>(out + (size_t)k * 2 * L + L, ay);
+    }
+}
+
+// out[i] = scalars[i] * B  (BatchMulPreprocessing::batch_mul, ec/src/scalar_mul/mod.rs:225-245): 32 table additions per scalar
+template <class PQ, class PR> __global__ void __launch_bounds__(64) batch_mul_kernel(const uint32_t *__restrict__ scalars, size_t n,
+                                                                                    const uint32_t *__restrict__ table, int windows,
+                                                                                    uint32_t *__restrict__ out) {
+    using E = Ec<PQ>;
+    using FR = Fp<PR>;
+    constexpr int L = PQ::L;
+    size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGenBatch;
+    if (i0 >= n) return;
+    typename E::B pts[kGenBatch];
+    int cnt = 0;
+    for (; cnt < kGenBatch && i0 + cnt < n; cnt++) {
+        uint32_t s[8], k[8];
+        load_limbs_nc<8>(s, scalars + (i0 + cnt) * 8);
+        FR::from_mont(k, s);
+        typename E::B acc;
+        E::xyzz_set_zero(acc);
+        for (int w = 0; w < windows; w++) {
+            uint32_t d = (k[w >> 2] >> (8 * (w & 3))) & 255u;
+            if (d == 0) continue;
+            uint32_t px[L], py[L];
+            const uint32_t *tp = table + (size_t)(w * 256 + d) * 2 * L;
+            load_limbs_nc<L>(px, tp);
+            load_limbs_nc<L>(py, tp + L);
+            E::madd(acc, px, py, false);
+        }
+        pts[cnt] = acc;
+    }
+    xyzz_batch_to_affine<PQ, kGenBatch>(pts, cnt, out + i0 * 2 * L);
+}
+
+// Projective::normalize_batch (group.rs:302-319): Jacobian (x,y,z) -> affine, z = 0 -> identity (0,0)
+template <class P> __global__ void __launch_bounds__(64) normalize_batch_kernel(const uint32_t *__restrict__ jac, size_t n, uint32_t *__restrict__ out) {
+    using F = Fp<P>;
+    constexpr int L = P::L;
+    size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGenBatch;
+    if (i0 >= n) return;
+    Xyzz<P> pts[kGenBatch];
+    int cnt = 0;
+    for (; cnt < kGenBatch && i0 + cnt < n; cnt++) {
+        const uint32_t *p = jac + (i0 + cnt) * 3 * L;
+        uint32_t z[L];
+        load_limbs<L>(pts[cnt].x, p);
+        load_limbs<L>(pts[cnt].y, p + L);
+        load_limbs<L>(z, p + 2 * L);
+        F::sqr(pts[cnt].zz, z);                                // Jacobian z  ->  XYZZ (zz, zzz) = (z^2, z^3)
+        F::mul(pts[cnt].zzz, pts[cnt].zz, z);
+    }
+    xyzz_batch_to_affine<P, kGenBatch>(pts, cnt, out + i0 * 2 * L);
+}
+
 static std::mutex g_table_mutex;
 static std::map<std::pair<int, int>, uint32_t *> g_tables;
 
@@ -150,6 +261,43 @@ int gen_scalars_dispatch(int field, uint64_t seed, size_t n, void *d_scalars, cu
     if (field == B200_FIELD_BLS12_381_FR) gen_scalars_kernel<BlsFr><<<blocks, 256, 0, st>>>(seed, n, (uint32_t *)d_scalars);
     else if (field == B200_FIELD_BN254_FR) gen_scalars_kernel<BnFr><<<blocks, 256, 0, st>>>(seed, n, (uint32_t *)d_scalars);
     else { set_last_error("unknown scalar field id"); return B200_EINVAL; }
+    AB_LAUNCHED();
+    return 0;
+}
+
+template <class PQ, class PR> static int batch_mul_run(const uint64_t *base_xy, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
+    constexpr int L = PQ::L;
+    const int windows = (PR::BITS + 7) / 8;
+    LimbArg<L> bx, by;
+    for (int i = 0; i < L / 2; i++) {
+        bx.v[2 * i] = (uint32_t)base_xy[i]; bx.v[2 * i + 1] = (uint32_t)(base_xy[i] >> 32);
+        by.v[2 * i] = (uint32_t)base_xy[L / 2 + i]; by.v[2 * i + 1] = (uint32_t)(base_xy[L / 2 + i] >> 32);
+    }
+    uint32_t *table = nullptr;
+    AB_CUDA(cudaMallocAsync(&table, (size_t)windows * 256 * 2 * L * 4, st));
+    batch_table_kernel<PQ><<<(windows * 256 + 63) / 64, 64, 0, st>>>(bx, by, windows, table);
+    AB_LAUNCHED();
+    size_t threads = (n + kGenBatch - 1) / kGenBatch;
+    batch_mul_kernel<PQ, PR><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((const uint32_t *)d_scalars, n, table, windows, (uint32_t *)d_out);
+    AB_LAUNCHED();
+    AB_CUDA(cudaFreeAsync(table, st));
+    return 0;
+}
+int batch_mul_dispatch(int curve, const uint64_t *base_xy, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
+    if (!base_xy || (n && (!d_scalars || !d_out))) { set_last_error("null pointer"); return B200_EINVAL; }
+    if (n == 0) return 0;
+    if (curve == B200_CURVE_BLS12_381) return batch_mul_run<BlsFq, BlsFr>(base_xy, d_scalars, n, d_out, st);
+    if (curve == B200_CURVE_BN254) return batch_mul_run<BnFq, BnFr>(base_xy, d_scalars, n, d_out, st);
+    set_last_error("unknown curve id");
+    return B200_EINVAL;
+}
+int normalize_batch_dispatch(int curve, const void *d_xyz, size_t n, void *d_out, cudaStream_t st) {
+    if (n && (!d_xyz || !d_out)) { set_last_error("null pointer"); return B200_EINVAL; }
+    if (n == 0) return 0;
+    size_t threads = (n + kGenBatch - 1) / kGenBatch;
+    if (curve == B200_CURVE_BLS12_381) normalize_batch_kernel<BlsFq><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((const uint32_t *)d_xyz, n, (uint32_t *)d_out);
+    else if (curve == B200_CURVE_BN254) normalize_batch_kernel<BnFq><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((const uint32_t *)d_xyz, n, (uint32_t *)d_out);
+    else { set_last_error("unknown curve id"); return B200_EINVAL; }
     AB_LAUNCHED();
     return 0;
 }

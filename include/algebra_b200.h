@@ -122,6 +122,14 @@ int b200_clear_cache(void);
 int b200_gen_bases_dev(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, void *stream);
 int b200_gen_scalars_dev(int field, uint64_t seed, size_t n, void *d_scalars, void *stream);
 
+/* Fixed-base batch multiplication and batch normalisation — the data-parallel steps that PRODUCE MSM bases (SRS powers):
+ *   b200_g1_batch_mul_dev        out[i] = scalars[i] * base   (BatchMulPreprocessing::batch_mul, ec/src/scalar_mul/mod.rs:156-245;
+ *                                8-bit fixed-base windows + batch inversion); base_xy: HOST, affine 2N u64; d_scalars n x 4 u64
+ *                                (Fr Montgomery); d_out_xy n x 2N u64 affine, identity = (0,0)
+ *   b200_g1_normalize_batch_dev  Projective::normalize_batch (ec/src/models/short_weierstrass/group.rs:302-319): n x 3N -> n x 2N */
+int b200_g1_batch_mul_dev(int curve, const uint64_t *base_xy, const void *d_scalars, size_t n, void *d_out_xy, void *stream);
+int b200_g1_normalize_batch_dev(int curve, const void *d_xyz, size_t n, void *d_out_xy, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Element-wise primitive kernels (parity tests and the field micro-benchmark, cf.
  * bench-templates/src/macros/field.rs:69-155).  Device pointers; 1 thread per element.

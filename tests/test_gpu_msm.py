@@ -286,3 +286,36 @@ def test_msm_bigint_and_small_scalar_entry_points():
     for i in range(300):
         cp.add(bh[i], canon[i])
     assert (ab.into_affine(cid, cp.finalize()) == ab.into_affine(cid, ab.msm(cid, bh[:300], sh[:300]))).all()
+
+
+@pytest.mark.parametrize("cid", [0, 1])
+def test_batch_mul_and_normalize_batch(cid):
+    """ScalarMul::batch_mul (ec/src/scalar_mul/mod.rs:156-245) and Projective::normalize_batch (group.rs:302-319),
+    cf. test-templates/src/groups.rs:222-255: limb-exact against the oracle."""
+    cv = O.CURVES[cid]
+    fr = cv.fr
+    rnd = random.Random(77 + cid)
+    n = 203                                              # not a multiple of the per-thread batch
+    sc = [rnd.randrange(fr.p) for _ in range(n)]
+    sc[0], sc[1], sc[2], sc[9] = 0, 1, fr.p - 1, 0       # zero scalars -> identity in the middle of a batch
+    base = cv.mul(cv.G, 0xABCDEF12345)
+    got = ab.batch_mul(cid, cv.encode_affine([base])[0], fr.encode(sc))
+    want = cv.encode_affine([cv.mul(base, s) for s in sc])
+    assert (got == want).all()
+    assert not got[0].any() and not got[9].any()
+    assert (ab.batch_mul(cid, cv.encode_affine([None])[0], fr.encode(sc[:5])) == 0).all()   # identity base
+    # normalize_batch on Jacobian points with non-trivial z, plus identities
+    pts = [cv.mul(cv.G, rnd.randrange(1, 1 << 50)) for _ in range(40)]
+    aff = cv.encode_affine(pts)
+    N = cv.fq.N
+    zero = np.zeros((1, 4 * N), dtype=np.uint64)
+    zero[0, :N] = cv.fq.limbs(cv.fq.R)
+    zero[0, N:2 * N] = cv.fq.limbs(cv.fq.R)
+    b = C.ec_op(cid, "madd", np.repeat(zero, 40, 0), aff)
+    b = C.ec_op(cid, "madd", b, np.roll(aff, 1, 0))
+    jac = C.ec_op(cid, "to_jac", b)
+    jac[7, 2 * N:] = 0                                    # an identity (z = 0)
+    jac[8, 2 * N:] = 0
+    got = ab.normalize_batch(cid, jac)
+    want = C.ec_op(cid, "jac_to_affine", jac)
+    assert (got == want).all() and not got[7].any()

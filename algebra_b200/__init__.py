@@ -6,7 +6,7 @@ from . import _lib, params                                    # noqa: F401
 from .radix2 import Radix2EvaluationDomain                    # noqa: F401
 from .polynomial import interpolate, poly_mul                  # noqa: F401
 from .fixed_base import batch_mul, normalize_batch             # noqa: F401
-from .variable_base import (ChunkedPippenger, LengthMismatch, into_affine, msm, msm_bigint, msm_chunks, msm_u1, msm_u8,   # noqa: F401
+from .variable_base import (ChunkedPippenger, HashMapPippenger, LengthMismatch, into_affine, msm, msm_bigint, msm_chunks, msm_u1, msm_u8,   # noqa: F401
                             msm_u16, msm_u32, msm_u64, msm_unchecked, sum_points)
 from .params import BLS12_381_G1, BN254_G1                    # noqa: F401
 

@@ -178,3 +178,35 @@ def last_timings() -> dict:
     d = {k: float(v) for k, v in zip(names, ms)}
     d.update(c=c.value, windows=w.value, bucket_adds=adds.value)
     return d
+
+
+class HashMapPippenger:
+    """stream_pippenger.rs:68-128: coalesce repeated bases (scalars of equal bases are added in Fr on the host) and
+    flush through msm_bigint every `buf_size` distinct bases."""
+
+    def __init__(self, curve: G1Curve | int, max_msm_buffer: int):
+        self.cv = CURVES[curve] if isinstance(curve, int) else curve
+        self.buf_size = max_msm_buffer
+        self.buffer: dict[bytes, int] = {}
+        self.results = []
+
+    def add(self, base, scalar):
+        """`scalar` is an Fr element as 4 Montgomery limbs (like G::ScalarField)"""
+        key = np.asarray(base, dtype=np.uint64).reshape(2 * self.cv.N).tobytes()
+        fr = self.cv.fr
+        self.buffer[key] = (self.buffer.get(key, 0) + fr.from_limbs(scalar)) % fr.modulus
+        if len(self.buffer) == self.buf_size:
+            self._flush()
+
+    def _flush(self):
+        bases = np.frombuffer(b"".join(self.buffer.keys()), dtype=np.uint64).reshape(-1, 2 * self.cv.N)
+        bigints = np.array([[(v >> (64 * i)) & ((1 << 64) - 1) for i in range(4)] for v in self.buffer.values()], dtype=np.uint64)
+        self.results.append(msm_bigint(self.cv, bases, bigints))      # `s.into_bigint()` = canonical limbs
+        self.buffer = {}
+
+    def finalize(self) -> np.ndarray:
+        if self.buffer:
+            self._flush()
+        if not self.results:
+            return msm_unchecked(self.cv, np.zeros((0, 2 * self.cv.N), np.uint64), np.zeros((0, 4), np.uint64))
+        return sum_points(self.cv, np.stack(self.results))

@@ -286,6 +286,12 @@ def test_msm_bigint_and_small_scalar_entry_points():
     for i in range(300):
         cp.add(bh[i], canon[i])
     assert (ab.into_affine(cid, cp.finalize()) == ab.into_affine(cid, ab.msm(cid, bh[:300], sh[:300]))).all()
+    # HashMapPippenger: repeated bases are coalesced before the MSM
+    hp = ab.HashMapPippenger(cid, 64)
+    order = [i % 90 for i in range(300)]
+    for j, i in enumerate(order):
+        hp.add(bh[i], sh[j])
+    assert (ab.into_affine(cid, hp.finalize()) == ab.into_affine(cid, ab.msm(cid, bh[order], sh[:300]))).all()
 
 
 @pytest.mark.parametrize("cid", [0, 1])

@@ -9,6 +9,7 @@ int msm_dispatch(int curve, int kind, const void *d_bases, const void *d_scalars
                  const size_t *chunk_off, const cudaEvent_t *ready);
 size_t scalar_kind_bytes(int kind);
 int msm_set_window(int c);
+int msm_set_affine_levels(int levels);
 int msm_auto_window(size_t n, int scalar_bits);
 int msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds);
 int g1_sum_dispatch(int curve, const uint64_t *pts_host, size_t k, uint64_t *out_host, bool to_affine);
@@ -86,6 +87,7 @@ int b200_msm_sw_g1_scalars(int curve, int scalar_kind, const uint64_t *bases, co
 }
 
 int b200_set_msm_window(int c) { return msm_set_window(c); }
+int b200_set_msm_affine_levels(int levels) { return msm_set_affine_levels(levels); }
 int b200_msm_window_for(int curve, size_t n) {
     if (curve != B200_CURVE_BLS12_381 && curve != B200_CURVE_BN254) return B200_EINVAL;
     return msm_auto_window(n, curve == B200_CURVE_BLS12_381 ? 255 : 254);

@@ -198,7 +198,9 @@ static constexpr uint32_t kNoBucket = 0xffffffffu;
 template <class P> __device__ __forceinline__ void store_xyzz(uint32_t *p, const Xyzz<P> &b);
 template <class P> __device__ __forceinline__ void load_xyzz(Xyzz<P> &b, const uint32_t *p);
 
-template <class C>
+// DIRECT = false: entry p is `sorted[p]` = (base index | sign<<31), gathered from `bases`;
+// DIRECT = true : entry p is the affine point stored at bases[p] (output of the batched-affine pre-reduction), no sign.
+template <class C, bool DIRECT>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                              const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t T,
                                                              uint32_t *__restrict__ buckets, uint32_t *__restrict__ head,
@@ -230,17 +232,17 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__r
     typename E::B acc;
     E::xyzz_set_zero(acc);
     uint32_t cx[L], cy[L], nx[L], ny[L];
-    uint32_t e = __ldg(sorted + lo), e_next = 0;
+    uint32_t e = DIRECT ? lo : __ldg(sorted + lo), e_next = 0;
     {
-        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
+        const uint32_t *bp = bases + (size_t)(DIRECT ? e : (e & 0x7fffffffu)) * (2 * L);
         load_limbs_nc<L>(cx, bp);
         load_limbs_nc<L>(cy, bp + L);
     }
     for (uint32_t pos = lo; pos < hi; pos++) {
         const bool more = (pos + 1 < hi);
         if (more) {  // issue the next gather before the ~10 modmuls of this addition
-            e_next = __ldg(sorted + pos + 1);
-            const uint32_t *bp = bases + (size_t)(e_next & 0x7fffffffu) * (2 * L);
+            e_next = DIRECT ? pos + 1 : __ldg(sorted + pos + 1);
+            const uint32_t *bp = bases + (size_t)(DIRECT ? e_next : (e_next & 0x7fffffffu)) * (2 * L);
             load_limbs_nc<L>(nx, bp);
             load_limbs_nc<L>(ny, bp + L);
         }
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__r
             started_before = false;
             do { b++; bucket_end = __ldg(offsets + b + 1); } while (bucket_end <= pos);
         }
-        E::madd(acc, cx, cy, (e >> 31) != 0);
+        E::madd(acc, cx, cy, !DIRECT && (e >> 31) != 0);
         if (more) {
             limbs_copy<L>(cx, nx);
             limbs_copy<L>(cy, ny);
@@ -271,6 +273,189 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__r
     }
     head_bucket[t] = hb;
     tail_bucket[t] = tb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched-affine pre-reduction (optional stage between the sort and the XYZZ accumulation).
+// One level halves every bucket's run: output slot j of bucket b = in[2j] + in[2j+1] (or in[2j] alone when the run is odd),
+// as AFFINE points.  Affine addition needs 1/(x2 - x1); a thread owns `batch` consecutive output slots and inverts all
+// their denominators with ONE field inversion (Montgomery's trick: forward pass stores the running products in the
+// output slots themselves, backward pass peels them off) — ~6 modmuls + inversion/batch per addition instead of the
+// 10 of an XYZZ mixed addition.  Degenerate pairs keep the batch intact with a denominator of 1: an identity operand passes
+// the other one through, equal points are doubled (denominator 2y), opposite points give the identity (0,0).
+// Same group element as the reference's bucket sums (EC addition is associative); parity is checked after into_affine().
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_halve_counts_kernel(const uint32_t *__restrict__ offsets_in, uint32_t total_buckets,
+                                                               uint32_t *__restrict__ counts_out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    uint32_t cnt = offsets_in[b + 1] - offsets_in[b];
+    counts_out[b] = (cnt + 1) >> 1;
+}
+
+template <class P, bool FIRST>
+__device__ __forceinline__ void pair_load_point(uint32_t *x, uint32_t *y, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
+                                                uint32_t k) {
+    constexpr int L = P::L;
+    if (FIRST) {
+        const uint32_t e = __ldg(src + k);
+        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
+        load_limbs_nc<L>(x, bp);
+        load_limbs_nc<L>(y, bp + L);
+        Fp<P>::cneg(y, y, (e >> 31) != 0);   // -(0,0) stays (0,0)
+    } else {
+        const uint32_t *bp = src + (size_t)k * (2 * L);
+        load_limbs_nc<L>(x, bp);
+        load_limbs_nc<L>(y, bp + L);
+    }
+}
+// x coordinate only (the forward pass needs y only for the rare degenerate pairs)
+template <class P, bool FIRST>
+__device__ __forceinline__ void pair_load_x(uint32_t *x, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src, uint32_t k) {
+    constexpr int L = P::L;
+    const uint32_t *bp = FIRST ? bases + (size_t)(__ldg(src + k) & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
+    load_limbs_nc<L>(x, bp);
+}
+
+enum { PAIR_PASS1 = 0, PAIR_PASS2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
+// classify (P1, P2) and produce the denominator of the slope (ONE for the degenerate kinds)
+template <class P> __device__ __forceinline__ int pair_classify(uint32_t *den, const uint32_t *x1, const uint32_t *y1, const uint32_t *x2,
+                                                                const uint32_t *y2, bool has2) {
+    using F = Fp<P>;
+    constexpr int L = P::L;
+    const bool z1 = limbs_is_zero<L>(x1) && limbs_is_zero<L>(y1);
+    const bool z2 = !has2 || (limbs_is_zero<L>(x2) && limbs_is_zero<L>(y2));
+    F::set_one(den);
+    if (z2) return PAIR_PASS1;            // also covers "both identity" (P1 = (0,0) passes through)
+    if (z1) return PAIR_PASS2;
+    if (limbs_eq<L>(x1, x2)) {
+        if (limbs_eq<L>(y1, y2) && !limbs_is_zero<L>(y1)) { F::dbl(den, y1); return PAIR_DBL; }
+        return PAIR_INF;
+    }
+    F::sub(den, x2, x1);
+    return PAIR_ADD;
+}
+
+// Latency hiding in this kernel is left to occupancy (128 registers -> 16 warps per SM).  Measured alternatives @2^26,
+// accumulation phase with 4 levels: plain loads 285 ms; next-slot operands held in registers (198 regs, 8 warps/SM) 329 ms;
+// prefetch.global.L2 of the next slot's operands (fetches whole 128-byte lines for 96-byte points) 346 ms.
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(128) msm_pair_add_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
+                                                           const uint32_t *__restrict__ offsets_in, const uint32_t *__restrict__ offsets_out,
+                                                           uint32_t total_buckets, uint32_t batch, uint32_t *__restrict__ out,
+                                                           uint32_t num_threads) {
+    using P = typename C::Fq;
+    using F = Fp<P>;
+    constexpr int L = P::L;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_threads) return;
+    const uint32_t M = __ldg(offsets_out + total_buckets);
+    const uint64_t lo64 = (uint64_t)t * batch;
+    if (lo64 >= M) return;
+    const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min((uint64_t)M, lo64 + batch);
+    uint32_t bl = 0, br = total_buckets;   // last b with offsets_out[b] <= lo
+    while (br - bl > 1) {
+        uint32_t mid = bl + ((br - bl) >> 1);
+        if (__ldg(offsets_out + mid) <= lo) bl = mid; else br = mid;
+    }
+    uint32_t x1[L], y1[L], x2[L], y2[L], den[L], run[L];
+    F::set_one(run);
+    // walk state = the bucket owning the NEXT slot (one ahead of the slot being computed)
+    uint32_t b = bl, out_end = __ldg(offsets_out + b + 1), out_beg = __ldg(offsets_out + b), in_beg = __ldg(offsets_in + b),
+             in_end = __ldg(offsets_in + b + 1);
+    // ---- forward: running product of the denominators, parked in the x-half of each output slot (x coordinates only)
+    uint32_t k = in_beg + 2 * (lo - out_beg);
+    bool has2 = k + 1 < in_end;
+    for (uint32_t p = lo; p < hi; p++) {
+        uint32_t kn = 0;
+        bool has2n = false;
+        if (p + 1 < hi) {
+            while (p + 1 >= out_end) {
+                b++;
+                out_beg = out_end;
+                out_end = __ldg(offsets_out + b + 1);
+                in_beg = __ldg(offsets_in + b);
+                in_end = __ldg(offsets_in + b + 1);
+            }
+            kn = in_beg + 2 * (p + 1 - out_beg);
+            has2n = kn + 1 < in_end;
+        }
+        if (has2) {
+            pair_load_x<P, FIRST>(x1, bases, src, k);
+            pair_load_x<P, FIRST>(x2, bases, src, k + 1);
+            if (limbs_is_zero<L>(x1) || limbs_is_zero<L>(x2) || limbs_eq<L>(x1, x2)) {   // rare: identity operand / equal x
+                pair_load_point<P, FIRST>(x1, y1, bases, src, k);
+                pair_load_point<P, FIRST>(x2, y2, bases, src, k + 1);
+                const int kind = pair_classify<P>(den, x1, y1, x2, y2, true);
+                if (kind >= PAIR_ADD) F::mul(run, run, den);
+            } else {
+                F::sub(den, x2, x1);
+                F::mul(run, run, den);
+            }
+        }
+        store_limbs<L>(out + (size_t)p * (2 * L), run);
+        k = kn;
+        has2 = has2n;
+    }
+    uint32_t inv[L];
+    F::inv(inv, run);
+    // ---- backward: peel the inverses off and write the sums; the walk state now sits on the bucket of slot hi-1
+    k = in_beg + 2 * (hi - 1 - out_beg);
+    has2 = k + 1 < in_end;
+    for (uint32_t p = hi; p-- > lo;) {
+        uint32_t kn = 0;
+        bool has2n = false;
+        if (p > lo) {
+            while (p - 1 < out_beg) {
+                b--;
+                out_end = out_beg;
+                out_beg = __ldg(offsets_out + b);
+                in_beg = __ldg(offsets_in + b);
+                in_end = __ldg(offsets_in + b + 1);
+            }
+            kn = in_beg + 2 * (p - 1 - out_beg);
+            has2n = kn + 1 < in_end;
+        }
+        pair_load_point<P, FIRST>(x1, y1, bases, src, k);
+        if (has2) pair_load_point<P, FIRST>(x2, y2, bases, src, k + 1);
+        const int kind = pair_classify<P>(den, x1, y1, x2, y2, has2);
+        uint32_t *o = out + (size_t)p * (2 * L);
+        if (kind >= PAIR_ADD) {
+            uint32_t dinv[L], lam[L], t3[L];
+            if (p > lo) { load_limbs<L>(t3, out + (size_t)(p - 1) * (2 * L)); F::mul(dinv, inv, t3); }   // inv * prefix_{p-1} = 1/den
+            else limbs_copy<L>(dinv, inv);
+            F::mul(inv, inv, den);
+            if (kind == PAIR_ADD) {
+                F::sub(lam, y2, y1);
+            } else {                      // doubling: slope = 3 x^2 / (2 y)
+                F::sqr(lam, x1);
+                F::dbl(t3, lam);
+                F::add(lam, lam, t3);
+                limbs_copy<L>(x2, x1);
+            }
+            F::mul(lam, lam, dinv);
+            F::sqr(t3, lam);
+            F::sub(t3, t3, x1);
+            F::sub(t3, t3, x2);           // x3
+            F::sub(x2, x1, t3);
+            F::mul(x2, lam, x2);
+            F::sub(x2, x2, y1);           // y3 = lam (x1 - x3) - y1
+            store_limbs<L>(o, t3);
+            store_limbs<L>(o + L, x2);
+        } else if (kind == PAIR_PASS1) {
+            store_limbs<L>(o, x1);
+            store_limbs<L>(o + L, y1);
+        } else if (kind == PAIR_PASS2) {
+            store_limbs<L>(o, x2);
+            store_limbs<L>(o + L, y2);
+        } else {
+            F::set_zero(x1);
+            store_limbs<L>(o, x1);
+            store_limbs<L>(o + L, x1);
+        }
+        k = kn;
+        has2 = has2n;
+    }
 }
 
 // bucket b = tail[t0] + head[t0+1] + ... + head[t1], t1 = task holding the bucket's last entry.
@@ -490,12 +675,19 @@ template <class C> __global__ void jac_to_affine_kernel(const uint32_t *__restri
 // host driver
 // ------------------------------------------------------------------------------------------------
 static thread_local int t_window_override = 0;
+static thread_local int t_affine_levels = -1;   // batched-affine pre-reduction levels; -1 = automatic
 struct MsmTimings {
     float ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int c = 0, W = 0;
     unsigned long long bucket_adds = 0;
 };
 static thread_local MsmTimings t_last;
+
+int msm_set_affine_levels(int levels) {
+    if (levels < -1 || levels > 6) { set_last_error("affine levels must be in [-1, 6]"); return B200_EINVAL; }
+    t_affine_levels = levels;
+    return 0;
+}
 
 int msm_set_window(int c) {
     if (c < 0 || c > 24) { set_last_error("window size must be in [1,24] (0 = automatic)"); return B200_EINVAL; }
@@ -585,6 +777,15 @@ template <class C> static int msm_run(const uint32_t *d_bases, const void *d_sca
     for (int k = 0; k < K; k++) n_max = std::max(n_max, coff[k + 1] - coff[k]);
     const size_t max_entries = n_max * (size_t)g.W;
     if (max_entries >= ((size_t)1 << 32)) { set_last_error("n * windows must be < 2^32"); return B200_ETOOLARGE; }
+    // batched-affine levels: automatic = keep halving while buckets still hold >= ~8 entries, at most 4 levels (measured
+    // at 2^26: 339 / 324 / 310 / 303 / 300 ms of accumulation for 0..4 levels), and only if the level-1 array fits comfortably
+    int levels = t_affine_levels;
+    if (levels < 0) {
+        const double load = (double)n_max / (double)g.nb;
+        levels = 0;
+        for (double l = load; l >= 16.0 && levels < 4; l *= 0.5) levels++;
+        if ((double)max_entries * 0.5 * 2 * L * 4 > 64e9) levels = 0;
+    }
 
     std::vector<cudaEvent_t> ev((size_t)K * 5 + 3);
     for (auto &e : ev) AB_CUDA(cudaEventCreate(&e));
@@ -652,16 +853,59 @@ template <class C> static int msm_run(const uint32_t *d_bases, const void *d_sca
         }
         AB_CUDA(cudaEventRecord(e[3], st));
         AB_CUDA(cudaMemsetAsync(target, 0, nb_total * 4 * L * 4, st));
-        const uint32_t num_tasks = (uint32_t)((nk * (size_t)g.W + T - 1) / T);
+        // optional batched-affine pre-reduction: each level halves the entries (as affine points) before the XYZZ accumulation
+        size_t cur_entries = nk * (size_t)g.W;   // upper bound on the entries of the current level
+        const uint32_t *cur_src = sorted, *cur_offsets = offsets;
+        uint32_t *lvl_pts[2] = {nullptr, nullptr}, *lvl_off[2] = {nullptr, nullptr};
+        int levels_done = 0;
+        for (int lv = 0; lv < levels && nk; lv++) {
+            // sum_b ceil(cnt_b / 2) <= min((entries + non-empty buckets) / 2, entries)
+            const size_t out_cap = std::min((cur_entries + nb_total) / 2 + 1, cur_entries);
+            uint32_t *pts = nullptr, *off2 = nullptr;
+            AB_CUDA(cudaMallocAsync(&pts, out_cap * 2 * L * 4, st));
+            AB_CUDA(cudaMallocAsync(&off2, (nb_total + 1) * 4, st));
+            msm_halve_counts_kernel<<<(unsigned)((nb_total + 255) / 256), 256, 0, st>>>(cur_offsets, (uint32_t)nb_total, counts);
+            AB_LAUNCHED();
+            scan_block_totals_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals);
+            AB_LAUNCHED();
+            scan_totals_kernel<<<1, kScanThreads, 0, st>>>(block_totals, scan_blocks);
+            AB_LAUNCHED();
+            scan_apply_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals, off2);
+            AB_LAUNCHED();
+            uint32_t batch = 1024;
+            while (batch > 32 && out_cap / batch < (1u << 16)) batch >>= 1;
+            const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);
+            if (lv == 0)
+                msm_pair_add_kernel<C, true><<<(nthreads + 127) / 128, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nb_total, batch, pts, nthreads);
+            else
+                msm_pair_add_kernel<C, false><<<(nthreads + 127) / 128, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nb_total, batch, pts, nthreads);
+            AB_LAUNCHED();
+            // the level before the previous one is no longer read
+            if (lvl_pts[lv & 1]) { AB_CUDA(cudaFreeAsync(lvl_pts[lv & 1], st)); AB_CUDA(cudaFreeAsync(lvl_off[lv & 1], st)); }
+            lvl_pts[lv & 1] = pts;
+            lvl_off[lv & 1] = off2;
+            cur_src = pts;
+            cur_offsets = off2;
+            cur_entries = out_cap;
+            levels_done++;
+        }
+        const uint32_t num_tasks = (uint32_t)((cur_entries + T - 1) / T);
+        if (num_tasks > max_tasks) { set_last_error("internal: task count exceeds scratch"); return B200_EINVAL; }
         if (num_tasks) {
-            msm_accumulate_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(bas, sorted, offsets, (uint32_t)nb_total, T, target, head, tail,
-                                                                            head_bucket, tail_bucket, num_tasks);
+            if (levels_done)
+                msm_accumulate_kernel<C, true><<<(num_tasks + 127) / 128, 128, 0, st>>>(cur_src, nullptr, cur_offsets, (uint32_t)nb_total, T, target, head,
+                                                                                      tail, head_bucket, tail_bucket, num_tasks);
+            else
+                msm_accumulate_kernel<C, false><<<(num_tasks + 127) / 128, 128, 0, st>>>(bas, sorted, offsets, (uint32_t)nb_total, T, target, head, tail,
+                                                                                       head_bucket, tail_bucket, num_tasks);
             AB_LAUNCHED();
-            msm_fixup_small_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, target);
+            msm_fixup_small_kernel<C><<<(num_tasks + 127) / 128, 128, 0, st>>>(cur_offsets, T, head, tail, tail_bucket, num_tasks, target);
             AB_LAUNCHED();
-            msm_fixup_big_kernel<C><<<num_tasks, 128, 128 * 4 * L * 4, st>>>(offsets, T, head, tail, tail_bucket, num_tasks, target);
+            msm_fixup_big_kernel<C><<<num_tasks, 128, 128 * 4 * L * 4, st>>>(cur_offsets, T, head, tail, tail_bucket, num_tasks, target);
             AB_LAUNCHED();
         }
+        for (int q = 0; q < 2; q++)
+            if (lvl_pts[q]) { AB_CUDA(cudaFreeAsync(lvl_pts[q], st)); AB_CUDA(cudaFreeAsync(lvl_off[q], st)); }
         if (k > 0) {
             msm_merge_kernel<C><<<(unsigned)((nb_total + 127) / 128), 128, 0, st>>>(buckets, extra, (uint32_t)nb_total);
             AB_LAUNCHED();

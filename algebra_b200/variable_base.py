@@ -165,6 +165,11 @@ def set_window(c: int) -> None:
     _lib.check(_lib.lib().b200_set_msm_window(c))
 
 
+def set_affine_levels(levels: int) -> None:
+    """batched-affine pre-reduction levels (0 = off, -1 = automatic); result-neutral tuning knob"""
+    _lib.check(_lib.lib().b200_set_msm_affine_levels(levels))
+
+
 def window_for(curve: G1Curve | int, n: int) -> int:
     cv = CURVES[curve] if isinstance(curve, int) else curve
     return _lib.lib().b200_msm_window_for(cv.cid, n)

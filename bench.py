@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--log-n-ntt", type=int, default=24)
     ap.add_argument("--curve", type=int, default=0, help="0 = BLS12-381 G1 (metric), 1 = BN254 G1")
     ap.add_argument("--window", type=int, default=0, help="Pippenger window override (0 = auto)")
+    ap.add_argument("--affine-levels", type=int, default=-1, help="batched-affine pre-reduction levels (-1 = auto)")
     ap.add_argument("--seed", type=int, default=20260922)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -219,6 +220,7 @@ def main():
     _lib.check(L.b200_gen_bases_dev(cv.cid, args.seed + 1000 * rank, n_local, d_bases.data_ptr(), d_b.data_ptr(), st))
     _lib.check(L.b200_gen_scalars_dev(cv.ntt_field_id, args.seed + 7777 + 1000 * rank, n_local, d_scal.data_ptr(), st))
     VB.set_window(args.window)
+    VB.set_affine_levels(args.affine_levels)
 
     from algebra_b200 import dist as D
 

@@ -79,6 +79,9 @@ int b200_msm_sw_g1_scalars_dev(int curve, int scalar_kind, const void *d_bases, 
  * yields the same group element.)  b200_msm_window_for(n) reports what "automatic" picks. */
 int b200_set_msm_window(int c);
 int b200_msm_window_for(int curve, size_t n);
+/* Number of batched-affine pre-reduction levels run between the sort and the XYZZ accumulation (each level halves the
+ * bucket runs with affine additions sharing one inversion per batch): 0 = off, -1 = automatic.  Result-neutral. */
+int b200_set_msm_affine_levels(int levels);
 
 /* sum of k Jacobian points (k x 3N u64, host) -> out_xyz: the local "reduce" after the multi-GPU
  * all-gather of per-rank partial sums (Projective::add_assign, group.rs:450-538). */

@@ -325,3 +325,48 @@ def test_batch_mul_and_normalize_batch(cid):
     got = ab.normalize_batch(cid, jac)
     want = C.ec_op(cid, "jac_to_affine", jac)
     assert (got == want).all() and not got[7].any()
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3, 5])
+def test_batched_affine_levels(levels):
+    """The batched-affine pre-reduction is result-neutral: random inputs, the mixed/adversarial set (identity bases,
+    repeated bases -> doubling inside a pair, P and -P adjacent -> identity inside a pair, all-equal scalars ->
+    runs of equal points) and short top windows all give the reference's group element."""
+    cid = 0
+    cv, fr = O.BLS12_381, O.BLS12_381_FR
+    try:
+        M.set_affine_levels(levels)
+        for n, seed in ((1 << 12, 11), (777, 12)):
+            d_bases, d_b, d_s = synth(cid, n, seed)
+            want = expected_from_b(cid, from_dev(d_b), from_dev(d_s))
+            for c in (0, 5, 9):
+                M.set_window(c)
+                assert (ab.into_affine(cid, ab.msm(cid, d_bases, d_s)) == want).all(), (n, c)
+            M.set_window(0)
+        # adversarial: all bases equal (every pair is a doubling), alternating P / -P (every pair cancels), identities
+        n = 1 << 10
+        d_bases, d_b, d_s = synth(cid, n, 99)
+        bh, bb = from_dev(d_bases).copy(), [int(x) for x in from_dev(d_b)]
+        sh = from_dev(d_s)
+        s0 = fr.decode(sh[:1])[0]
+        same_s = np.repeat(sh[:1], n, axis=0)
+        same_b = np.repeat(bh[:1], n, axis=0)
+        want = cv.encode_affine([cv.mul(cv.G, bb[0] * s0 * n % fr.p)])[0]
+        assert (ab.into_affine(cid, ab.msm(cid, same_b, same_s)) == want).all()
+        alt = same_b.copy()
+        alt[1::2] = cv.encode_affine([cv.neg(cv.decode_affine(bh[:1])[0])])[0]
+        assert (ab.into_affine(cid, ab.msm(cid, alt, same_s)) == 0).all()
+        alt[::3] = 0                                                  # identity bases sprinkled in
+        keep = sum((1 if i % 2 == 0 else -1) for i in range(n) if i % 3 != 0)
+        want = cv.encode_affine([cv.mul(cv.G, bb[0] * s0 * keep % fr.p)])[0]
+        assert (ab.into_affine(cid, ab.msm(cid, alt, same_s)) == want).all()
+        # all-equal scalars over distinct bases with a short top window
+        M.set_window(18)
+        d_bases, d_b, _ = synth(cid, 1 << 13, 5)
+        bb = [int(x) for x in from_dev(d_b)]
+        sh = np.repeat(fr.encode([fr.p - 2]), 1 << 13, axis=0)
+        want = cv.encode_affine([cv.mul(cv.G, (fr.p - 2) * sum(bb) % fr.p)])[0]
+        assert (ab.into_affine(cid, ab.msm(cid, d_bases, to_dev(sh))) == want).all()
+    finally:
+        M.set_window(0)
+        M.set_affine_levels(-1)

@@ -20,6 +20,7 @@
 // 2^(c-1), and 2^(lambda-(W-1)c) for the top window.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -339,8 +340,8 @@ template <class P> __device__ __forceinline__ int pair_classify(uint32_t *den, c
 // Latency hiding in this kernel is left to occupancy (128 registers -> 16 warps per SM).  Measured alternatives @2^26,
 // accumulation phase with 4 levels: plain loads 285 ms; next-slot operands held in registers (198 regs, 8 warps/SM) 329 ms;
 // prefetch.global.L2 of the next slot's operands (fetches whole 128-byte lines for 96-byte points) 346 ms.
-template <class C, bool FIRST>
-__global__ void __launch_bounds__(128) msm_pair_add_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
+template <class C, bool FIRST, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_pair_add_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
                                                            const uint32_t *__restrict__ offsets_in, const uint32_t *__restrict__ offsets_out,
                                                            uint32_t total_buckets, uint32_t batch, uint32_t *__restrict__ out,
                                                            uint32_t num_threads) {
@@ -875,10 +876,11 @@ template <class C> static int msm_run(const uint32_t *d_bases, const void *d_sca
             uint32_t batch = 1024;
             while (batch > 32 && out_cap / batch < (1u << 16)) batch >>= 1;
             const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);
-            if (lv == 0)
-                msm_pair_add_kernel<C, true><<<(nthreads + 127) / 128, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nb_total, batch, pts, nthreads);
-            else
-                msm_pair_add_kernel<C, false><<<(nthreads + 127) / 128, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nb_total, batch, pts, nthreads);
+            // 128 threads x 4 resident blocks (128 registers, no spills) measured best: forcing 5 / 6 blocks per SM (96 / 80
+            // registers with spills) gave 324 / 345 ms of accumulation instead of 286 ms @2^26
+            const unsigned pg = (nthreads + 127) / 128;
+            if (lv == 0) msm_pair_add_kernel<C, true, 4><<<pg, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nb_total, batch, pts, nthreads);
+            else msm_pair_add_kernel<C, false, 4><<<pg, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nb_total, batch, pts, nthreads);
             AB_LAUNCHED();
             // the level before the previous one is no longer read
             if (lvl_pts[lv & 1]) { AB_CUDA(cudaFreeAsync(lvl_pts[lv & 1], st)); AB_CUDA(cudaFreeAsync(lvl_off[lv & 1], st)); }

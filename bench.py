@@ -375,15 +375,17 @@ def main():
                        "l2": "inputs (>= 2 GiB) larger than L2; no flush needed", "seed": args.seed, "verified_vs_sum_identity": verified},
             "clocks": clocks,
             "phases_ms": phase,
-            "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": byts / acc_s / 1e9 if acc_s else None,
+            "roofline": {"bound": "hbm", "kernel": "accumulation phase: msm_pair_add_kernel (batched-affine levels) + msm_accumulate_kernel", "achieved": byts / acc_s / 1e9 if acc_s else None,
                          "peak": hbm_peak, "unit": "GB/s", "frac": (byts / acc_s / 1e9) / hbm_peak if acc_s else None,
                          "traffic": None, "peak_source": peak_src,
                          "note": "compute-bound kernel: see imad_roofline (SURVEY.md §8d: MSM is bound by the integer-multiply pipe)"},
-            "imad_roofline": {"bound": "int32 wide-MAD pipe", "kernel": "msm_accumulate_kernel",
+            "imad_roofline": {"bound": "int32 wide-MAD pipe", "kernel": "accumulation phase: msm_pair_add_kernel + msm_accumulate_kernel",
                               "achieved": acc_wide / acc_s / 1e12 if acc_s else None, "peak": IMAD_PEAK_WIDE_PER_S / 1e12,
                               "unit": "T wide-MAD/s", "frac": (acc_wide / acc_s) / IMAD_PEAK_WIDE_PER_S if acc_s else None,
                               "peak_source": "measured microbench (profiles/r01_imad_microbench.jsonl)",
-                              "algorithmic": "10 Fq modmuls x (2L^2+L = 300) wide MADs per bucket addition, n*W additions"},
+                              "algorithmic": "10 Fq modmuls x (2L^2+L = 300) wide MADs per bucket addition, n*W additions (the reference's "
+                                             "XYZZ formula); the batched-affine levels execute ~6.6 modmuls for 15/16 of the additions, "
+                                             "so this fraction can exceed 1"},
             "gpu_launches": launches,
             "e2e": e2e,
             "cpu_baseline": cpu,

@@ -968,8 +968,9 @@ int msm_dispatch(int curve, int kind, const void *d_bases, const void *d_scalars
     ch.ready = ready;
     // device-resident inputs too large for one 32-bit entry index space (n * windows >= 2^32): split into equal chunks
     std::vector<size_t> auto_off;
-    if (K <= 1 && n > ((size_t)1 << 27)) {
-        const int kk = (int)((n + ((size_t)1 << 27) - 1) >> 27);
+    const char *force = getenv("B200_MSM_FORCE_CHUNKS");   // test hook: exercise the chunked device path at small n
+    if (K <= 1 && (n > ((size_t)1 << 27) || (force && atoi(force) > 1 && n >= 64))) {
+        const int kk = n > ((size_t)1 << 27) ? (int)((n + ((size_t)1 << 27) - 1) >> 27) : atoi(force);
         for (int k = 0; k <= kk; k++) auto_off.push_back(n * (size_t)k / kk);
         ch.K = kk;
         ch.offset = auto_off.data();

@@ -370,3 +370,16 @@ def test_batched_affine_levels(levels):
     finally:
         M.set_window(0)
         M.set_affine_levels(-1)
+
+
+def test_chunked_device_path(monkeypatch):
+    """Device-resident inputs beyond 2^27 pairs are processed as several chunks merged bucket-wise; the hook
+    B200_MSM_FORCE_CHUNKS exercises that path at a testable size."""
+    cid, n = 0, 5000
+    d_bases, d_b, d_s = synth(cid, n, 321)
+    want = expected_from_b(cid, from_dev(d_b), from_dev(d_s))
+    for k in ("3", "7"):
+        monkeypatch.setenv("B200_MSM_FORCE_CHUNKS", k)
+        assert (ab.into_affine(cid, ab.msm(cid, d_bases, d_s)) == want).all()
+    monkeypatch.delenv("B200_MSM_FORCE_CHUNKS")
+    assert (ab.into_affine(cid, ab.msm(cid, d_bases, d_s)) == want).all()

@@ -707,7 +707,7 @@ int msm_auto_window(size_t n, int scalar_bits) {
         MsmGeom g = make_geom(c, scalar_bits);
         if ((double)g.total_buckets * 192.0 > 24e9) continue;
         const double entries = (double)n * g.W;
-        double t = 0.39 * entries + 2.6 * (double)g.total_buckets + 0.02 * entries;
+        double t = 0.33 * entries + 2.6 * (double)g.total_buckets + 0.02 * entries;   // 0.33: with the batched-affine levels (0.39 without)
         if (g.top_bits < 10) t += 0.15 * (double)n;   // hot top-window buckets serialise the atomics
         // tiny inputs: keep enough accumulation tasks (>= 8 entries each) to fill the machine
         t += 2000.0 * g.W;                             // per-window fixed costs (reduction tree, combine doublings)
@@ -862,6 +862,12 @@ template <class C> static int msm_run(const uint32_t *d_bases, const void *d_sca
         for (int lv = 0; lv < levels && nk; lv++) {
             // sum_b ceil(cnt_b / 2) <= min((entries + non-empty buckets) / 2, entries)
             const size_t out_cap = std::min((cur_entries + nb_total) / 2 + 1, cur_entries);
+            // one inversion (~570 modmuls) per `batch` additions: never below 256 in automatic mode, where a level that cannot
+            // fill the machine with 256-slot threads is left to the XYZZ kernel instead
+            const bool forced = t_affine_levels >= 0;
+            uint32_t batch = 1024;
+            while (batch > (forced ? 32u : 256u) && out_cap / batch < (1u << 16)) batch >>= 1;
+            if (!forced && out_cap / batch < (1u << 14)) break;
             uint32_t *pts = nullptr, *off2 = nullptr;
             AB_CUDA(cudaMallocAsync(&pts, out_cap * 2 * L * 4, st));
             AB_CUDA(cudaMallocAsync(&off2, (nb_total + 1) * 4, st));
@@ -873,8 +879,6 @@ template <class C> static int msm_run(const uint32_t *d_bases, const void *d_sca
             AB_LAUNCHED();
             scan_apply_kernel<<<(unsigned)scan_blocks, kScanThreads, 0, st>>>(counts, nb_total, block_totals, off2);
             AB_LAUNCHED();
-            uint32_t batch = 1024;
-            while (batch > 32 && out_cap / batch < (1u << 16)) batch >>= 1;
             const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);
             // 128 threads x 4 resident blocks (128 registers, no spills) measured best: forcing 5 / 6 blocks per SM (96 / 80
             // registers with spills) gave 324 / 345 ms of accumulation instead of 286 ms @2^26

@@ -30,7 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IMAD_PEAK_WIDE_PER_S = 8.5e12   # measured on this pool: profiles/r01_imad_microbench.jsonl (IMAD.WIDE.U32.X carry chains)
+# IMAD.WIDE.U32(.X) issues at 32 per clock per SM on B200 (tools/imad_microbench.cu, profiles/r01_imad_microbench.jsonl):
+# 32 x 148 SMs x 1.965 GHz = 9.31 T/s; the element-wise Fq multiplication kernel reaches 9.05 T/s of it
+# (profiles/r01_field_bench.jsonl), the synthetic carry-chain microbenchmark 8.5 T/s.
+IMAD_PEAK_WIDE_PER_S = 9.31e12
 
 
 def measured_peaks():
@@ -382,7 +385,7 @@ def main():
             "imad_roofline": {"bound": "int32 wide-MAD pipe", "kernel": "accumulation phase: msm_pair_add_kernel + msm_accumulate_kernel",
                               "achieved": acc_wide / acc_s / 1e12 if acc_s else None, "peak": IMAD_PEAK_WIDE_PER_S / 1e12,
                               "unit": "T wide-MAD/s", "frac": (acc_wide / acc_s) / IMAD_PEAK_WIDE_PER_S if acc_s else None,
-                              "peak_source": "measured microbench (profiles/r01_imad_microbench.jsonl)",
+                              "peak_source": "32 IMAD.WIDE/clk/SM measured (profiles/r01_imad_microbench.jsonl) x 148 SMs x 1.965 GHz",
                               "algorithmic": "10 Fq modmuls x (2L^2+L = 300) wide MADs per bucket addition, n*W additions (the reference's "
                                              "XYZZ formula); the batched-affine levels execute ~6.6 modmuls for 15/16 of the additions, "
                                              "so this fraction can exceed 1"},

@@ -126,7 +126,18 @@ int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const ui
     if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     return rc;
 }
-int b200_clear_cache(void) { return ntt_clear_cache(); }
+int b200_clear_cache(void) {
+    int rc = ntt_clear_cache();
+    // also hand the stream-ordered scratch retained by the default memory pool back to the driver (a 2^26 MSM keeps tens
+    // of GB of level buffers cached for the next call otherwise)
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    return rc;
+}
 
 size_t b200_poly_mul_size(int field, size_t la, size_t lb) {
     if ((field != B200_FIELD_BLS12_381_FR && field != B200_FIELD_BN254_FR) || la == 0 || lb == 0) return 0;

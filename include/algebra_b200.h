@@ -111,7 +111,7 @@ int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const 
 size_t b200_poly_mul_size(int field, size_t la, size_t lb);
 int b200_poly_mul_fr(int field, const uint64_t *a, size_t la, const uint64_t *b, size_t lb, uint64_t *out);
 int b200_poly_mul_fr_dev(int field, const void *d_a, size_t la, const void *d_b, size_t lb, void *d_out, void *stream);
-/* drop cached twiddle tables / scratch of the current device */
+/* drop cached twiddle tables of the current device and return the scratch retained by its default memory pool */
 int b200_clear_cache(void);
 
 /* ---------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 // capi.cu — the extern "C" boundary declared in include/algebra_b200.h.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ab200 {
@@ -55,13 +56,26 @@ int b200_msm_sw_g1_scalars(int curve, int scalar_kind, const uint64_t *bases, co
         AB_CUDA(cudaStreamCreateWithFlags(&streams[dev][1], cudaStreamNonBlocking));
     }
     cudaStream_t st = streams[dev][0], copy_st = streams[dev][1];
-    const int K = n >= ((size_t)1 << 22) ? 4 : 1;
-    size_t off[5];
-    cudaEvent_t ready[4], alloc_done;
-    // growing chunks (1/8, 1/8, 1/4, 1/2): only the first, small transfer is exposed; every later one is shorter than the
-    // arithmetic of the chunk before it
-    static const int kEighths[5] = {0, 1, 2, 4, 8};
-    for (int k = 0; k <= K; k++) off[k] = K == 1 ? (size_t)k * n : n / 8 * kEighths[k];
+    // chunk boundaries in 16ths of n.  Growing chunks: only the first, small transfer is exposed and every later one is
+    // shorter than the arithmetic of the chunk before it; few chunks, because small chunks run the accumulation less
+    // efficiently (short bucket runs) and each extra chunk costs a bucket-merge pass.  B200_MSM_CHUNKS="2,8,16" overrides (tuning knob).
+    int bounds[9] = {0, 2, 4, 8, 16, 0, 0, 0, 0};   // 1/8, 1/8, 1/4, 1/2 (measured: e2e 511 -> 417 ms @2^26)
+    int K = n >= ((size_t)1 << 22) ? 4 : 1;
+    if (const char *e = getenv("B200_MSM_CHUNKS")) {
+        int k = 0, v = 0;
+        const char *q = e;
+        while (*q && k < 8) {
+            v = atoi(q);
+            if (v <= bounds[k] || v > 16) break;
+            bounds[++k] = v;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        if (k >= 1 && bounds[k] == 16 && n >= 1024) K = k;
+    }
+    size_t off[9];
+    cudaEvent_t ready[8], alloc_done;
+    for (int k = 0; k <= K; k++) off[k] = K == 1 ? (size_t)k * n : n / 16 * (size_t)bounds[k];
     off[K] = n;
     void *d_bases = nullptr, *d_scalars = nullptr;
     AB_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));

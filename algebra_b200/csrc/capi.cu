@@ -59,8 +59,9 @@ int b200_msm_sw_g1_scalars(int curve, int scalar_kind, const uint64_t *bases, co
     // chunk boundaries in 16ths of n.  Growing chunks: only the first, small transfer is exposed and every later one is
     // shorter than the arithmetic of the chunk before it; few chunks, because small chunks run the accumulation less
     // efficiently (short bucket runs) and each extra chunk costs a bucket-merge pass.  B200_MSM_CHUNKS="2,8,16" overrides (tuning knob).
-    int bounds[9] = {0, 2, 4, 8, 16, 0, 0, 0, 0};   // 1/8, 1/8, 1/4, 1/2 (measured: e2e 511 -> 417 ms @2^26)
-    int K = n >= ((size_t)1 << 22) ? 4 : 1;
+    // measured @2^26 (e2e ms): {2,7,16} 404, {2,6,16} 405, {2,8,16} 418, {2,4,8,16} 419, {4,16} 432, {3,16} 447, unchunked 511
+    int bounds[9] = {0, 2, 7, 16, 0, 0, 0, 0, 0};
+    int K = n >= ((size_t)1 << 22) ? 3 : 1;
     if (const char *e = getenv("B200_MSM_CHUNKS")) {
         int k = 0, v = 0;
         const char *q = e;

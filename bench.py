@@ -176,8 +176,6 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
 

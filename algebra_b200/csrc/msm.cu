@@ -1,23 +1,23 @@
-// msm.cu — variable-base MSM over short-Weierstrass G1 (a = 0) for sm_100a: bucket method (Pippenger) with
-// signed c-bit digits, counting-sort bucket assignment and task-balanced XYZZ accumulation.
+// msm.cu — variable-base MSM over short-Weierstrass G1 (a = 0) for sm_100a: bucket method (Pippenger) with signed c-bit
+// digits, counting-sort bucket assignment, batched-affine pre-reduction and task-balanced XYZZ accumulation.
 //
 // Replaces VariableBaseMSM::msm_unchecked for Projective<P> (ec/src/scalar_mul/variable_base/mod.rs:59-64
 // -> msm_bigint_wnaf_parallel :437-503).  Same mathematics, GPU schedule:
 //   reference (per window, serial over points)          here (all windows at once)
-//   into_bigint + make_digits (:60-62, :754-794)    ->  msm_digits_kernel<HIST>: REDC + signed digits, histogram of
-//                                                       (window, |digit|) with global atomics
-//   buckets[|d|-1] +=/-= base  (:467-475)           ->  exclusive scan of the histogram, msm_digits_kernel<SCATTER>
-//                                                       writes (index | sign) into bucket-sorted order, then
-//                                                       msm_accumulate_kernel: one thread per task of T sorted entries runs the
-//                                                       reference's `Bucket += Affine` (bucket.rs:168-238), flushing per bucket
-//   running-sum  res += running_sum (:478-484)      ->  msm_bucket_reduce_kernel: each thread does the running sum over a
-//                                                       chunk of m buckets plus (chunk offset) * (chunk total);
-//                                                       msm_sum_partials_kernel tree-adds the chunks of a window
+//   into_bigint + make_digits (:60-62, :754-794)    ->  msm_digits_kernel<HIST>: REDC + signed digits, histogram of (window, |digit|)
+//   buckets[|d|-1] +=/-= base  (:467-475)           ->  exclusive scan; msm_digits_kernel<SCATTER> writes (index | sign) in bucket order;
+//                                                       msm_pair_add_kernel x up to 4 levels: every bucket run is halved with AFFINE
+//                                                       additions that share one inversion per batch (Montgomery's trick);
+//                                                       msm_accumulate_kernel: one thread per task of T entries runs the reference's
+//                                                       `Bucket += Affine` (bucket.rs:168-238) on what is left, flushing per bucket;
+//                                                       msm_fixup_*: buckets that span tasks
+//   running-sum  res += running_sum (:478-484)      ->  msm_bucket_reduce_kernel (running sum per chunk of 32 buckets + chunk offset times
+//                                                       chunk total) and msm_sum_partials_kernel (tree over the chunks of a window)
 //   window combine, c doublings per window (:489-502) -> msm_window_combine_kernel (Jacobian, one thread)
-// EC addition is commutative/associative, so bucket order, atomics and chunking do not change the group element;
+// EC addition is commutative/associative, so bucket order, atomics, pairing and chunking do not change the group element;
 // results are compared with the reference after into_affine(), limb-exact.
-// The digit recoding is the reference's make_digits (top window unsigned), so bucket counts per window are
-// 2^(c-1), and 2^(lambda-(W-1)c) for the top window.
+// The digit recoding is the reference's make_digits (top window unsigned), so bucket counts per window are 2^(c-1), and
+// 2^(lambda-(W-1)c) for the top window.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

@@ -24,6 +24,17 @@ SIGNATURES = {
     "b200_msm_sw_g1_dev": (_c.c_int, [_c.c_int, _vp, _vp, _c.c_size_t, _vp, _vp]),
     "b200_msm_sw_g1_scalars": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _c.c_size_t, _vp]),
     "b200_msm_sw_g1_scalars_dev": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _c.c_size_t, _vp, _vp]),
+    "b200_msm_sw_g2": (_c.c_int, [_vp, _vp, _c.c_size_t, _vp]),
+    "b200_msm_sw_g2_dev": (_c.c_int, [_vp, _vp, _c.c_size_t, _vp, _vp]),
+    "b200_device_count": (_c.c_int, []),
+    "b200_msm_sw_g1_multi": (_c.c_int, [_c.c_int, _c.c_int, _vp, _vp, _c.c_size_t, _vp]),
+    "b200_bases_upload": (_c.c_int, [_c.c_int, _c.c_int, _vp, _c.c_size_t, _c.POINTER(_vp)]),
+    "b200_msm_bases": (_c.c_int, [_vp, _c.c_int, _vp, _c.c_size_t, _vp]),
+    "b200_bases_free": (_c.c_int, [_vp]),
+    "b200_msm_stream_begin": (_c.c_int, [_c.c_int, _c.c_int, _c.c_size_t, _c.c_size_t, _c.POINTER(_vp)]),
+    "b200_msm_stream_push": (_c.c_int, [_vp, _vp, _vp, _c.c_size_t]),
+    "b200_msm_stream_finish": (_c.c_int, [_vp, _vp]),
+    "b200_msm_stream_abort": (_c.c_int, [_vp]),
     "b200_set_msm_window": (_c.c_int, [_c.c_int]),
     "b200_set_msm_affine_levels": (_c.c_int, [_c.c_int]),
     "b200_msm_window_for": (_c.c_int, [_c.c_int, _c.c_size_t]),

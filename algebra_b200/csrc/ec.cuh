@@ -12,21 +12,23 @@
 // Affine infinity is (0,0) (ZeroFlag = (), short_weierstrass/mod.rs:224-230).
 #pragma once
 #include "fp.cuh"
+#include "fp2.cuh"
 
 namespace ab200 {
 
-template <class P> struct Xyzz {
-    uint32_t x[P::L], y[P::L], zz[P::L], zzz[P::L];
+template <int L> struct Xyzz {
+    uint32_t x[L], y[L], zz[L], zzz[L];
 };
-template <class P> struct Jac {
-    uint32_t x[P::L], y[P::L], z[P::L];
+template <int L> struct Jac {
+    uint32_t x[L], y[L], z[L];
 };
 
-template <class P> struct Ec {
-    static constexpr int L = P::L;
-    using F = Fp<P>;
-    using B = Xyzz<P>;
-    using J = Jac<P>;
+// FT = the coordinate field's operations class: Fp<P> (G1, L = P::L words per coordinate) or Fp2<P> (G2, L = 2*P::L).
+template <class FT> struct Ec {
+    using F = FT;
+    static constexpr int L = F::L;
+    using B = Xyzz<L>;
+    using J = Jac<L>;
 
     static AB_HD void xyzz_set_zero(B &b) {
         F::set_one(b.x);

@@ -44,7 +44,7 @@ template <class P> __global__ void gen_scalars_kernel(uint64_t seed, size_t n, u
 
 // table[w*256 + d] = (d * 256^w) * G, affine Montgomery (d = 0 -> (0,0))
 template <class P> __global__ void gen_table_kernel(uint32_t *table) {
-    using E = Ec<P>;
+    using E = Ec<Fp<P>>;
     using F = Fp<P>;
     constexpr int L = P::L;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +68,7 @@ template <class P> __global__ void gen_table_kernel(uint32_t *table) {
 
 template <class P> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64_t seed, size_t n, const uint32_t *__restrict__ table,
                                                                          uint32_t *__restrict__ bases, uint64_t *__restrict__ bvals) {
-    using E = Ec<P>;
+    using E = Ec<Fp<P>>;
     using F = Fp<P>;
     constexpr int L = P::L;
     size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGenBatch;
@@ -114,7 +114,7 @@ template <class P> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64
 // table[w*256 + d] = (d * 256^w) * B for an arbitrary affine base B, w < windows  (BatchMulPreprocessing::new,
 // ec/src/scalar_mul/mod.rs:163-215, with an 8-bit window)
 template <class P> __global__ void batch_table_kernel(LimbArg<P::L> bx, LimbArg<P::L> by, int windows, uint32_t *table) {
-    using E = Ec<P>;
+    using E = Ec<Fp<P>>;
     constexpr int L = P::L;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= windows * 256) return;
@@ -138,8 +138,8 @@ template <class P> __global__ void batch_table_kernel(LimbArg<P::L> bx, LimbArg<
 }
 
 // XYZZ points of one thread -> affine with ONE inversion (Montgomery's trick, ff/src/fields/mod.rs:358-420); identity -> (0,0)
-template <class P, int B> __device__ __forceinline__ void xyzz_batch_to_affine(Xyzz<P> *pts, int cnt, uint32_t *out /* cnt x 2L */) {
-    using E = Ec<P>;
+template <class P, int B> __device__ __forceinline__ void xyzz_batch_to_affine(Xyzz<P::L> *pts, int cnt, uint32_t *out /* cnt x 2L */) {
+    using E = Ec<Fp<P>>;
     using F = Fp<P>;
     constexpr int L = P::L;
     uint32_t prefix[B][L], run[L];
@@ -173,7 +173,7 @@ template <class P, int B> __device__ __forceinline__ void xyzz_batch_to_affine(X
 template <class PQ, class PR> __global__ void __launch_bounds__(64) batch_mul_kernel(const uint32_t *__restrict__ scalars, size_t n,
                                                                                     const uint32_t *__restrict__ table, int windows,
                                                                                     uint32_t *__restrict__ out) {
-    using E = Ec<PQ>;
+    using E = Ec<Fp<PQ>>;
     using FR = Fp<PR>;
     constexpr int L = PQ::L;
     size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGenBatch;
@@ -206,7 +206,7 @@ template <class P> __global__ void __launch_bounds__(64) normalize_batch_kernel(
     constexpr int L = P::L;
     size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGenBatch;
     if (i0 >= n) return;
-    Xyzz<P> pts[kGenBatch];
+    Xyzz<P::L> pts[kGenBatch];
     int cnt = 0;
     for (; cnt < kGenBatch && i0 + cnt < n; cnt++) {
         const uint32_t *p = jac + (i0 + cnt) * 3 * L;

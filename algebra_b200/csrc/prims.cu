@@ -32,7 +32,7 @@ template <class P> __global__ void fp_op_kernel(int op, const uint32_t *a, const
 }
 
 template <class P> __global__ void ec_op_kernel(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
-    using E = Ec<P>;
+    using E = Ec<Fp<P>>;
     constexpr int L = P::L;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -52,7 +52,8 @@ def _msm_kind(curve: G1Curve | int, kind: int, bases, scalars) -> np.ndarray:
         import torch
         if not (bases.is_cuda and scalars.is_cuda and bases.is_contiguous() and scalars.is_contiguous()):
             raise TypeError("device path needs contiguous CUDA tensors")
-        assert bases.element_size() == 8 and scalars.element_size() == np.dtype(dtype).itemsize
+        if bases.element_size() != 8 or scalars.element_size() != np.dtype(dtype).itemsize:
+            raise TypeError("device path: bases must be 8-byte integers and scalars must match the scalar kind's width")
         with torch.cuda.device(bases.device):
             st = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().b200_msm_sw_g1_scalars_dev(cv.cid, kind, bases.data_ptr(), scalars.data_ptr(), n, outp, st))
@@ -94,27 +95,64 @@ def msm_u64(curve, bases, scalars) -> np.ndarray:
     return _msm_kind(curve, _lib.SCALARS_U64, bases, scalars)
 
 
+class MsmStream:
+    """b200_msm_stream_*: one set of buckets for a stream of chunks.  Every push is copied to the device while the previous
+    chunk is still being accumulated; the bucket reduction and the window combine run once, in finish()."""
+
+    def __init__(self, curve: G1Curve | int, max_chunk: int, n_total_hint: int = 0, kind: int = _lib.SCALARS_FR_MONT):
+        self.cv = CURVES[curve] if isinstance(curve, int) else curve
+        self.kind = kind
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().b200_msm_stream_begin(self.cv.cid, kind, n_total_hint, max(1, max_chunk), ctypes.byref(self._h)))
+
+    def push(self, bases, scalars) -> None:
+        dtype, width = _KIND_DTYPE[self.kind]
+        b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * self.cv.N)
+        s = np.ascontiguousarray(scalars, dtype=dtype).reshape(-1, width)
+        n = min(len(b), len(s))
+        if self._h is None:
+            raise RuntimeError("stream already finished")
+        _lib.check(_lib.lib().b200_msm_stream_push(self._h, b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), n))
+
+    def finish(self) -> np.ndarray:
+        out = np.zeros(3 * self.cv.N, dtype=np.uint64)
+        h, self._h = self._h, None
+        _lib.check(_lib.lib().b200_msm_stream_finish(h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().b200_msm_stream_abort(self._h)
+            self._h = None
+
+
 def msm_chunks(curve: G1Curve | int, bases_stream, scalars_stream, step: int = 1 << 20) -> np.ndarray:
     """VariableBaseMSM::msm_chunks (:119-150): the scalar stream may be shorter than the base stream; the LAST
-    len(scalars) bases are used (`skip(bases.len() - scalars.len())`), folded `step` pairs at a time."""
+    len(scalars) bases are used (`skip(bases.len() - scalars.len())`), consumed `step` pairs at a time through the
+    streaming C ABI (one bucket set, one reduction at the end — the reference folds a full MSM per chunk)."""
     cv = CURVES[curve] if isinstance(curve, int) else curve
     nb, ns = _rows(bases_stream, 2 * cv.N), _rows(scalars_stream, 4)
-    assert ns <= nb, "scalars_stream.len() <= bases_stream.len()"
-    b = bases_stream.reshape(-1, 2 * cv.N)[nb - ns:]
-    s = scalars_stream.reshape(-1, 4)
-    parts = [msm_unchecked(cv, b[lo:lo + step], s[lo:lo + step]) for lo in range(0, ns, step)]
-    if not parts:
+    if ns > nb:
+        raise ValueError("scalars_stream.len() <= bases_stream.len()")
+    b = np.asarray(bases_stream).reshape(-1, 2 * cv.N)[nb - ns:]
+    s = np.asarray(scalars_stream).reshape(-1, 4)
+    if ns == 0:
         return msm_unchecked(cv, b[:0], s[:0])
-    return parts[0] if len(parts) == 1 else sum_points(cv, np.stack(parts))
+    st = MsmStream(cv, min(step, ns), ns)
+    for lo in range(0, ns, step):
+        st.push(b[lo:lo + step], s[lo:lo + step])
+    return st.finish()
 
 
 class ChunkedPippenger:
-    """stream_pippenger.rs:10-66: buffer (base, bigint scalar) pairs, flush through msm_bigint every `buf_size`."""
+    """stream_pippenger.rs:10-66: buffer (base, bigint scalar) pairs, hand every full buffer of `buf_size` pairs to the device
+    (b200_msm_stream_push with canonical BigInt scalars) and finalize once."""
 
     def __init__(self, curve: G1Curve | int, max_msm_buffer: int):
         self.cv = CURVES[curve] if isinstance(curve, int) else curve
         self.buf_size = max_msm_buffer
-        self.bases, self.scalars, self.results = [], [], []
+        self.bases, self.scalars = [], []
+        self._stream = None
 
     def add(self, base, scalar_bigint):
         self.bases.append(np.asarray(base, dtype=np.uint64).reshape(2 * self.cv.N))
@@ -123,15 +161,64 @@ class ChunkedPippenger:
             self._flush()
 
     def _flush(self):
-        self.results.append(msm_bigint(self.cv, np.stack(self.bases), np.stack(self.scalars)))
+        if self._stream is None:
+            self._stream = MsmStream(self.cv, self.buf_size, 0, _lib.SCALARS_BIGINT)
+        self._stream.push(np.stack(self.bases), np.stack(self.scalars))
         self.bases, self.scalars = [], []
 
     def finalize(self) -> np.ndarray:
         if self.scalars:
             self._flush()
-        if not self.results:
+        if self._stream is None:
             return msm_unchecked(self.cv, np.zeros((0, 2 * self.cv.N), np.uint64), np.zeros((0, 4), np.uint64))
-        return sum_points(self.cv, np.stack(self.results))
+        st, self._stream = self._stream, None
+        return st.finish()
+
+
+def device_count() -> int:
+    return _lib.lib().b200_device_count()
+
+
+def msm_multi(curve: G1Curve | int, bases, scalars, ngpus: int) -> np.ndarray:
+    """b200_msm_sw_g1_multi: host arrays in, one process drives `ngpus` devices (input-chunk sharding, partial sums added on
+    device 0).  Same truncation rule as msm_unchecked."""
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * cv.N)
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    n = min(len(b), len(s))
+    out = np.zeros(3 * cv.N, dtype=np.uint64)
+    _lib.check(_lib.lib().b200_msm_sw_g1_multi(cv.cid, ngpus, b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), n,
+                                               out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+class BasesHandle:
+    def __init__(self, cv, h, n):
+        self.cv, self.h, self.n = cv, h, n
+
+
+def bases_upload(curve: G1Curve | int, bases, ngpus: int = 1) -> BasesHandle:
+    """b200_bases_upload: keep `bases` resident in HBM (sharded over `ngpus` devices) across MSM calls."""
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 2 * cv.N)
+    h = ctypes.c_void_p()
+    _lib.check(_lib.lib().b200_bases_upload(cv.cid, ngpus, b.ctypes.data_as(ctypes.c_void_p), len(b), ctypes.byref(h)))
+    return BasesHandle(cv, h, len(b))
+
+
+def msm_with_bases(handle: BasesHandle, scalars, kind: int = _lib.SCALARS_FR_MONT) -> np.ndarray:
+    dtype, width = _KIND_DTYPE[kind]
+    s = np.ascontiguousarray(scalars, dtype=dtype).reshape(-1, width)
+    n = min(len(s), handle.n)
+    out = np.zeros(3 * handle.cv.N, dtype=np.uint64)
+    _lib.check(_lib.lib().b200_msm_bases(handle.h, kind, s.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def bases_free(handle: BasesHandle) -> None:
+    if handle.h is not None:
+        _lib.lib().b200_bases_free(handle.h)
+        handle.h = None
 
 
 def msm(curve: G1Curve | int, bases, scalars) -> np.ndarray:
@@ -193,7 +280,7 @@ class HashMapPippenger:
         self.cv = CURVES[curve] if isinstance(curve, int) else curve
         self.buf_size = max_msm_buffer
         self.buffer: dict[bytes, int] = {}
-        self.results = []
+        self._stream = None
 
     def add(self, base, scalar):
         """`scalar` is an Fr element as 4 Montgomery limbs (like G::ScalarField)"""
@@ -206,12 +293,15 @@ class HashMapPippenger:
     def _flush(self):
         bases = np.frombuffer(b"".join(self.buffer.keys()), dtype=np.uint64).reshape(-1, 2 * self.cv.N)
         bigints = np.array([[(v >> (64 * i)) & ((1 << 64) - 1) for i in range(4)] for v in self.buffer.values()], dtype=np.uint64)
-        self.results.append(msm_bigint(self.cv, bases, bigints))      # `s.into_bigint()` = canonical limbs
+        if self._stream is None:
+            self._stream = MsmStream(self.cv, self.buf_size, 0, _lib.SCALARS_BIGINT)
+        self._stream.push(bases, bigints)      # `s.into_bigint()` = canonical limbs
         self.buffer = {}
 
     def finalize(self) -> np.ndarray:
         if self.buffer:
             self._flush()
-        if not self.results:
+        if self._stream is None:
             return msm_unchecked(self.cv, np.zeros((0, 2 * self.cv.N), np.uint64), np.zeros((0, 4), np.uint64))
-        return sum_points(self.cv, np.stack(self.results))
+        st, self._stream = self._stream, None
+        return st.finish()

@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-ntt", action="store_true", help="skip the NTT leg (MSM tuning runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -320,6 +321,14 @@ def main():
     # ---------------- NTT leg (replicas only for N > 1)
     del d_bases, d_b, d_scal
     torch.cuda.empty_cache()
+    if args.no_ntt:
+        if rank == 0:
+            print(json.dumps({"metric": "msm-only tuning run", "value": 1000.0 / ms_msm, "unit": "MSM/s", "ms_per_step": ms_msm,
+                              "phases_ms": phase, "window_c": tm["c"], "windows": tm["windows"], "verified": verified,
+                              "e2e": e2e, "clocks": clocks, "gpu_launches": launches}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n_ntt = 1 << args.log_n_ntt
     dom = ab.Radix2EvaluationDomain.new(cv.ntt_field_id, n_ntt)
     d_x = torch.empty((n_ntt, 4), dtype=torch.int64, device=dev)

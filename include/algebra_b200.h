@@ -29,9 +29,11 @@
 extern "C" {
 #endif
 
-/* curve ids (G1 only)            reference parameters                                         */
-#define B200_CURVE_BLS12_381 0 /* curves/bls12_381/src/curves/g1.rs:28-95                      */
-#define B200_CURVE_BN254 1     /* curves/bn254/src/curves/g1.rs:16-90                          */
+/* group ids                      reference parameters                                         */
+#define B200_CURVE_BLS12_381 0 /* G1: curves/bls12_381/src/curves/g1.rs:28-95                  */
+#define B200_CURVE_BN254 1     /* G1: curves/bn254/src/curves/g1.rs:16-90                      */
+#define B200_CURVE_BLS12_381_G2 2 /* G2: curves/bls12_381/src/curves/g2.rs:54; coordinates in Fq2 = (c0, c1), each 6 u64
+                                   * (ff/src/fields/models/quadratic_extension.rs:105-113), i.e. "N" = 12 u64 per coordinate */
 /* scalar-field ids for the NTT */
 #define B200_FIELD_BLS12_381_FR 0 /* curves/bls12_381/src/fields/fr.rs, TWO_ADICITY = 32        */
 #define B200_FIELD_BN254_FR 1     /* curves/bn254/src/fields/fr.rs,     TWO_ADICITY = 28        */
@@ -73,6 +75,40 @@ int b200_msm_sw_g1_dev(int curve, const void *d_bases, const void *d_scalars, si
 int b200_msm_sw_g1_scalars(int curve, int scalar_kind, const uint64_t *bases, const void *scalars, size_t n, uint64_t *out_xyz);
 int b200_msm_sw_g1_scalars_dev(int curve, int scalar_kind, const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz,
                                void *stream);
+
+/* G2 of BLS12-381 through the same pipeline (SWCurveConfig::msm hook of g2::Config, same file:line as above): affine points are
+ * x.c0, x.c1, y.c0, y.c1 (24 u64), the result is a Jacobian point over Fq2 (36 u64).  b200_g1_sum / b200_g1_into_affine accept
+ * B200_CURVE_BLS12_381_G2 as well (36 -> 24 u64). */
+int b200_msm_sw_g2(const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out_xyz);
+int b200_msm_sw_g2_dev(const void *d_bases, const void *d_scalars, size_t n, uint64_t *out_xyz, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU and resident-bases entry points: ONE process, one host thread + two streams per device, no torch, no NCCL —
+ * the partial sums come back to the host as 3N u64 each and are added on device 0 (Projective::add_assign).  This is what a
+ * Rust caller of `SWCurveConfig::msm` (ec/src/models/short_weierstrass/mod.rs:111-119) binds to use every GPU of the node.
+ *   ngpus   1 .. b200_device_count(); the n pairs are split into ngpus contiguous shards
+ * Host buffers may be pinned or pageable: pageable memory is staged through a per-device ring of pinned buffers filled by
+ * several host threads, so the PCIe copy of one slice overlaps the memcpy of the next.
+ * --------------------------------------------------------------------------------------------- */
+int b200_device_count(void);
+int b200_msm_sw_g1_multi(int curve, int ngpus, const uint64_t *bases, const uint64_t *scalars, size_t n, uint64_t *out_xyz);
+/* Bases uploaded once and kept in HBM (sharded over ngpus devices), the analogue of holding `&[G1Affine]` (an SRS) across
+ * calls; b200_msm_bases then moves only the scalars (n <= the handle's size; the first n bases are used, like msm_unchecked). */
+typedef struct b200_bases b200_bases_t;
+int b200_bases_upload(int curve, int ngpus, const uint64_t *bases, size_t n, b200_bases_t **handle);
+int b200_msm_bases(const b200_bases_t *handle, int scalar_kind, const void *scalars, size_t n, uint64_t *out_xyz);
+int b200_bases_free(b200_bases_t *handle);
+
+/* Streaming MSM — `VariableBaseMSM::msm_chunks` (ec/src/scalar_mul/variable_base/mod.rs:119-150) and `ChunkedPippenger`
+ * (stream_pippenger.rs:10-66) without a full reduce per chunk: every pushed chunk is copied (H2D of chunk k+1 under the
+ * arithmetic of chunk k), digit-sorted and accumulated into ONE set of buckets; the bucket reduction and window combine run
+ * once in finish.  n_total_hint (0 = unknown -> max_chunk) picks the window; every push must have n <= max_chunk.
+ * finish and abort release the handle. */
+typedef struct b200_msm_stream b200_msm_stream_t;
+int b200_msm_stream_begin(int curve, int scalar_kind, size_t n_total_hint, size_t max_chunk, b200_msm_stream_t **stream);
+int b200_msm_stream_push(b200_msm_stream_t *stream, const uint64_t *bases, const void *scalars, size_t n);
+int b200_msm_stream_finish(b200_msm_stream_t *stream, uint64_t *out_xyz);
+int b200_msm_stream_abort(b200_msm_stream_t *stream);
 
 /* Pippenger window size c used by subsequent MSM calls on this thread's device: 0 = automatic.
  * (The reference's rule is ln_without_floats(n)+2, ec/src/scalar_mul/variable_base/mod.rs:445-449; any c

@@ -127,6 +127,32 @@ def test_full_size_properties(log_n):
     assert (fxs[rows] == C.fp_op(ofid, "add", np.ascontiguousarray(fx[rows]), np.ascontiguousarray(fs[rows]))).all()
 
 
+def test_baseline_size_2e24_elementwise_vs_oracle():
+    """BASELINE.json configs[2] at n = 2^24: fft and ifft compared with the restated reference algorithm on EVERY element
+    (poly/src/domain/radix2/mod.rs:351-391 at full size), device-resident and host-buffer entry points."""
+    fr, ofid = FR[0]
+    log_n = 24
+    n = 1 << log_n
+    x = rand_limbs(fr, n, 2424)
+    x[0] = fr.encode([fr.p - 1])[0]
+    x[n - 1] = 0
+    thr = C.num_threads()
+    want = C.fft(ofid, x, False, None, threads=thr)
+    dom = ab.Radix2EvaluationDomain.new(0, n)
+    t = to_dev(x)
+    dom.fft_in_place(t)
+    assert (from_dev(t) == want).all()
+    dom.ifft_in_place(t)
+    assert (from_dev(t) == x).all()
+    want_inv = C.fft(ofid, x, True, None, threads=thr)
+    assert (dom.ifft(x) == want_inv).all()          # host-buffer entry (H2D + D2H inside the call)
+    del want_inv
+    off = fr.encode([fr.generator])
+    t = to_dev(x)
+    dom.get_coset(fr.generator).fft_in_place(t)
+    assert (from_dev(t) == C.fft(ofid, x, False, off, threads=thr)).all()
+
+
 def test_poly_mul_and_interpolate():
     """DensePolynomial * DensePolynomial (dense.rs:641-656) vs schoolbook multiplication with Python ints, host and
     device-resident paths; Evaluations::interpolate = ifft + trimming."""

@@ -29,7 +29,7 @@ template <class P> static int fp_op(int op, const uint32_t *a, const uint32_t *b
 }
 template <class P> static int ec_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
     constexpr int L = P::L;
-    using E = Ec<P>;
+    using E = Ec<Fp<P>>;
     for (size_t i = 0; i < n; i++) {
         typename E::B x, y; typename E::J j, k;
         switch (op) {

@@ -24,120 +24,9 @@
 #include <memory>
 #include <vector>
 
-#include "common.cuh"
-#include "ec.cuh"
+#include "msm_common.cuh"
 
 namespace ab200 {
-
-// Curve traits: F = operations class of the coordinate field (Fp<P> for G1, Fp2<P> for G2), Fr = scalar-field parameter pack.
-// (BlsFqRolled — Montgomery rows in a real loop, 4.6k instead of 7.6k SASS instructions — was measured SLOWER on B200:
-// accumulate 338 -> 371 ms @2^26; the unrolled rows let ptxas interleave six carry chains.)
-struct CurveBls {
-    using F = Fp<BlsFq>;
-    using Fr = BlsFr;
-    static constexpr int SCALAR_BITS = 255;  // Fr::MODULUS_BIT_SIZE (variable_base/mod.rs:451)
-    static constexpr bool AUTO_LEVELS = true;
-    static constexpr int PAIR_MINB = 4;      // resident blocks per SM the pair-add kernels are compiled for (128 registers)
-};
-struct CurveBn {
-    using F = Fp<BnFq>;
-    using Fr = BnFr;
-    static constexpr int SCALAR_BITS = 254;
-    // 8-limb coordinates: the affine additions are 2.2x cheaper in multiplies but move almost as many bytes, and the levels
-    // measured slower (BN254 2^24: 49 -> 55 ms), so the automatic mode keeps them for the 12-limb field only
-    static constexpr bool AUTO_LEVELS = false;
-    static constexpr int PAIR_MINB = 4;
-};
-// G2 of BLS12-381: coordinates in Fq2 (curves/bls12_381/src/curves/g2.rs:54), same scalar field
-struct CurveBlsG2 {
-    using F = Fp2<BlsFq>;
-    using Fr = BlsFr;
-    static constexpr int SCALAR_BITS = 255;
-    static constexpr bool AUTO_LEVELS = false;
-    static constexpr int PAIR_MINB = 2;      // 24-word coordinates: 255 registers, two blocks per SM
-};
-
-struct MsmGeom {
-    int c, W, top_bits;          // window bits, number of windows, bits in the top window
-    uint32_t nb;                 // buckets per non-top window = 2^(c-1)
-    uint32_t nb_top;             // buckets in the top window   = 2^top_bits
-    uint32_t total_buckets;      // (W-1)*nb + nb_top
-};
-
-static MsmGeom make_geom(int c, int scalar_bits) {
-    MsmGeom g;
-    g.c = c;
-    g.W = (scalar_bits + c - 1) / c;  // digits_count (:452)
-    g.top_bits = scalar_bits - (g.W - 1) * c;
-    g.nb = 1u << (c - 1);
-    g.nb_top = 1u << g.top_bits;
-    g.total_buckets = (uint32_t)(g.W - 1) * g.nb + g.nb_top;
-    return g;
-}
-
-// ------------------------------------------------------------------------------------------------
-// digits: canonical scalar -> signed digits (make_digits, :754-794); MODE 0 = histogram, 1 = scatter
-// ------------------------------------------------------------------------------------------------
-template <class C, int MODE>
-__global__ void __launch_bounds__(256) msm_digits_kernel(const void *__restrict__ scalars_v, int kind, size_t n, MsmGeom g, int w_lo, int w_hi,
-                                                         uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
-    using FR = Fp<typename C::Fr>;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t k[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) k[j] = 0;
-    if (kind <= B200_SCALARS_BIGINT) {
-        uint32_t s[8];
-        load_limbs_nc<8>(s, (const uint32_t *)scalars_v + i * 8);
-        if (kind == B200_SCALARS_FR_MONT) FR::from_mont(k, s);  // into_bigint (:60-62)
-        else limbs_copy<8>(k, s);                               // msm_bigint: already canonical (:80-85)
-    } else if (kind == B200_SCALARS_U8) k[0] = ((const uint8_t *)scalars_v)[i];
-    else if (kind == B200_SCALARS_U16) k[0] = ((const uint16_t *)scalars_v)[i];
-    else if (kind == B200_SCALARS_U32) k[0] = ((const uint32_t *)scalars_v)[i];
-    else { uint2 v = ((const uint2 *)scalars_v)[i]; k[0] = v.x; k[1] = v.y; }
-    // msm_signed's negative classes (variable_base/mod.rs:251-336): a scalar whose r - k fits 64 bits (NegU1..NegU64) is
-    // handled as -(r - k), i.e. the point enters with the opposite sign and only ceil(64/c) windows are non-zero
-    uint32_t flip = 0;
-    if (kind <= B200_SCALARS_BIGINT && (k[2] | k[3] | k[4] | k[5] | k[6] | k[7])) {
-        using R = typename C::Fr;
-        uint32_t t[8];
-        t[0] = ptx::sub_cc(R::MOD(0), k[0]);
-#pragma unroll
-        for (int j = 1; j < 8; j++) t[j] = ptx::subc_cc(R::MOD(j), k[j]);
-        const uint32_t borrow = ptx::subc(0u, 0u);   // non-zero iff k > r (non-canonical msm_bigint input: left alone)
-        if (!borrow && !(t[2] | t[3] | t[4] | t[5] | t[6] | t[7])) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) k[j] = t[j];
-            flip = 1;
-        }
-    }
-    const int c = g.c;
-    const uint32_t mask = (1u << c) - 1, half = 1u << (c - 1);
-    uint32_t carry = 0;
-    for (int w = 0; w < w_hi; w++) {  // the carry chain needs every lower window; only [w_lo, w_hi) is emitted
-        const int bit = w * c, wi = bit >> 5, sh = bit & 31;
-        uint64_t two = ((uint64_t)k[wi + 1] << 32) | k[wi];
-        uint32_t coef = ((uint32_t)(two >> sh) & mask) + carry;
-        uint32_t mag, neg = 0;
-        if (w == g.W - 1) {  // top digit stays unsigned (:789-791); bits above the declared scalar width are ignored
-            mag = (((uint32_t)(two >> sh) & mask) & ((1u << g.top_bits) - 1)) + carry;
-        } else {
-            carry = (coef + half) >> c;
-            if (carry) { mag = (1u << c) - coef; neg = 1; }  // digit = coef - 2^c in [-2^(c-1), 0)
-            else mag = coef;
-        }
-        if (mag && w >= w_lo) {
-            uint32_t gid = (uint32_t)w * g.nb + (mag - 1);
-            if (MODE == 0) {
-                atomicAdd(&counts_or_cursor[gid], 1u);
-            } else {
-                uint32_t pos = atomicAdd(&counts_or_cursor[gid], 1u);
-                sorted[pos] = (uint32_t)i | ((neg ^ flip) << 31);
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // exclusive scan of u32 counts (total < 2^32): block totals -> serial scan of totals -> apply
@@ -213,100 +102,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
         if (base + k == n - 1) out[n] = ex;
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// bucket accumulation — the hot loop (Bucket += Affine, bucket.rs:168-238), balanced by construction:
-// the bucket-sorted entry array is cut into tasks of exactly T consecutive entries, one thread per task, whatever the
-// bucket sizes are (a scalar distribution that piles everything into one bucket, or a short top window with 8 buckets
-// holding n/8 points each, costs the same as the uniform case).  A thread walks its slice and flushes an accumulator at
-// every bucket boundary: buckets that begin and end inside the slice are written straight to `buckets`; the piece of a
-// bucket that began in an earlier task goes to head[t], the piece of a bucket that continues into the next task to tail[t].
-// msm_fixup_* then add tail[t0] + head[t0+1..t1] for every bucket that spans tasks.  `buckets` is pre-zeroed (zz = zzz = 0
-// is the XYZZ identity) so empty buckets need no writer.
-// ------------------------------------------------------------------------------------------------
-static constexpr uint32_t kNoBucket = 0xffffffffu;
-
-template <int L> __device__ __forceinline__ void store_xyzz(uint32_t *p, const Xyzz<L> &b);
-template <int L> __device__ __forceinline__ void load_xyzz(Xyzz<L> &b, const uint32_t *p);
-
-// DIRECT = false: entry p is `sorted[p]` = (base index | sign<<31), gathered from `bases`;
-// DIRECT = true : entry p is the affine point stored at bases[p] (output of the batched-affine pre-reduction), no sign.
-template <class C, bool DIRECT>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                             const uint32_t *__restrict__ offsets, uint32_t total_buckets, uint32_t T,
-                                                             uint32_t *__restrict__ buckets, uint32_t *__restrict__ head,
-                                                             uint32_t *__restrict__ tail, uint32_t *__restrict__ head_bucket,
-                                                             uint32_t *__restrict__ tail_bucket, uint32_t num_tasks) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_tasks) return;
-    // `offsets` may be a window group's slice of a larger offsets array: entry positions start at offsets[0]
-    const uint32_t M = __ldg(offsets + total_buckets);
-    const uint64_t lo64 = (uint64_t)__ldg(offsets) + (uint64_t)t * T;
-    if (lo64 >= M) {
-        head_bucket[t] = kNoBucket;
-        tail_bucket[t] = kNoBucket;
-        return;
-    }
-    const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min((uint64_t)M, lo64 + T);
-    // b = last index with offsets[b] <= lo  (=> offsets[b] <= lo < offsets[b+1])
-    uint32_t bl = 0, br = total_buckets;  // invariant: offsets[bl] <= lo, offsets[br] > lo (offsets[total] = M > lo)
-    while (br - bl > 1) {
-        uint32_t mid = bl + ((br - bl) >> 1);
-        if (__ldg(offsets + mid) <= lo) bl = mid; else br = mid;
-    }
-    uint32_t b = bl, bucket_end = __ldg(offsets + b + 1);
-    bool started_before = __ldg(offsets + b) < lo;
-    uint32_t hb = kNoBucket;
-
-    typename E::B acc;
-    E::xyzz_set_zero(acc);
-    uint32_t cx[L], cy[L], nx[L], ny[L];
-    uint32_t e = DIRECT ? lo : __ldg(sorted + lo), e_next = 0;
-    {
-        const uint32_t *bp = bases + (size_t)(DIRECT ? e : (e & 0x7fffffffu)) * (2 * L);
-        load_limbs_nc<L>(cx, bp);
-        load_limbs_nc<L>(cy, bp + L);
-    }
-    for (uint32_t pos = lo; pos < hi; pos++) {
-        const bool more = (pos + 1 < hi);
-        if (more) {  // issue the next gather before the ~10 modmuls of this addition
-            e_next = DIRECT ? pos + 1 : __ldg(sorted + pos + 1);
-            const uint32_t *bp = bases + (size_t)(DIRECT ? e_next : (e_next & 0x7fffffffu)) * (2 * L);
-            load_limbs_nc<L>(nx, bp);
-            load_limbs_nc<L>(ny, bp + L);
-        }
-        if (pos == bucket_end) {  // bucket b is complete: flush, move to the (non-empty) bucket that owns `pos`
-            if (started_before) { store_xyzz<L>(head + (size_t)t * (4 * L), acc); hb = b; }
-            else store_xyzz<L>(buckets + (size_t)b * (4 * L), acc);
-            E::xyzz_set_zero(acc);
-            started_before = false;
-            do { b++; bucket_end = __ldg(offsets + b + 1); } while (bucket_end <= pos);
-        }
-        E::madd(acc, cx, cy, !DIRECT && (e >> 31) != 0);
-        if (more) {
-            limbs_copy<L>(cx, nx);
-            limbs_copy<L>(cy, ny);
-            e = e_next;
-        }
-    }
-    uint32_t tb = kNoBucket;
-    if (bucket_end == hi) {  // the last bucket ends exactly with the slice
-        if (started_before) { store_xyzz<L>(head + (size_t)t * (4 * L), acc); hb = b; }
-        else store_xyzz<L>(buckets + (size_t)b * (4 * L), acc);
-    } else if (started_before) {  // the whole slice is an inner piece of one bucket
-        store_xyzz<L>(head + (size_t)t * (4 * L), acc);
-        hb = b;
-    } else {
-        store_xyzz<L>(tail + (size_t)t * (4 * L), acc);
-        tb = b;
-    }
-    head_bucket[t] = hb;
-    tail_bucket[t] = tb;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Batched-affine pre-reduction (optional stage between the sort and the XYZZ accumulation).
 // One level halves every bucket's run: output slot j of bucket b = in[2j] + in[2j+1] (or in[2j] alone when the run is odd),
@@ -324,413 +119,6 @@ __global__ void __launch_bounds__(256) msm_halve_counts_kernel(const uint32_t *_
     uint32_t cnt = offsets_in[b + 1] - offsets_in[b];
     counts_out[b] = (cnt + 1) >> 1;
 }
-
-template <class F, bool FIRST>
-__device__ __forceinline__ void pair_load_point(uint32_t *x, uint32_t *y, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
-                                                uint32_t k) {
-    constexpr int L = F::L;
-    if (FIRST) {
-        const uint32_t e = __ldg(src + k);
-        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
-        load_limbs_nc<L>(x, bp);
-        load_limbs_nc<L>(y, bp + L);
-        F::cneg(y, y, (e >> 31) != 0);   // -(0,0) stays (0,0)
-    } else {
-        const uint32_t *bp = src + (size_t)k * (2 * L);
-        load_limbs_nc<L>(x, bp);
-        load_limbs_nc<L>(y, bp + L);
-    }
-}
-// x coordinate only (the forward pass needs y only for the rare degenerate pairs)
-template <class F, bool FIRST>
-__device__ __forceinline__ void pair_load_x(uint32_t *x, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src, uint32_t k) {
-    constexpr int L = F::L;
-    const uint32_t *bp = FIRST ? bases + (size_t)(__ldg(src + k) & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
-    load_limbs_nc<L>(x, bp);
-}
-
-enum { PAIR_PASS1 = 0, PAIR_PASS2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
-// classify (P1, P2) and produce the denominator of the slope (ONE for the degenerate kinds)
-template <class F> __device__ __forceinline__ int pair_classify(uint32_t *den, const uint32_t *x1, const uint32_t *y1, const uint32_t *x2,
-                                                                const uint32_t *y2, bool has2) {
-    constexpr int L = F::L;
-    const bool z1 = limbs_is_zero<L>(x1) && limbs_is_zero<L>(y1);
-    const bool z2 = !has2 || (limbs_is_zero<L>(x2) && limbs_is_zero<L>(y2));
-    F::set_one(den);
-    if (z2) return PAIR_PASS1;            // also covers "both identity" (P1 = (0,0) passes through)
-    if (z1) return PAIR_PASS2;
-    if (limbs_eq<L>(x1, x2)) {
-        if (limbs_eq<L>(y1, y2) && !limbs_is_zero<L>(y1)) { F::dbl(den, y1); return PAIR_DBL; }
-        return PAIR_INF;
-    }
-    F::sub(den, x2, x1);
-    return PAIR_ADD;
-}
-
-// Latency hiding in this kernel is left to occupancy (128 registers -> 16 warps per SM).  Measured alternatives @2^26,
-// accumulation phase with 4 levels: plain loads 285 ms; next-slot operands held in registers (198 regs, 8 warps/SM) 329 ms;
-// prefetch.global.L2 of the next slot's operands (fetches whole 128-byte lines for 96-byte points) 346 ms.
-template <class C, bool FIRST, int MINB>
-__global__ void __launch_bounds__(128, MINB) msm_pair_add_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
-                                                           const uint32_t *__restrict__ offsets_in, const uint32_t *__restrict__ offsets_out,
-                                                           uint32_t total_buckets, uint32_t batch, uint32_t *__restrict__ out,
-                                                           uint32_t num_threads) {
-    using F = typename C::F;
-    constexpr int L = F::L;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_threads) return;
-    const uint32_t M = __ldg(offsets_out + total_buckets);
-    const uint64_t lo64 = (uint64_t)t * batch;
-    if (lo64 >= M) return;
-    const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min((uint64_t)M, lo64 + batch);
-    uint32_t bl = 0, br = total_buckets;   // last b with offsets_out[b] <= lo
-    while (br - bl > 1) {
-        uint32_t mid = bl + ((br - bl) >> 1);
-        if (__ldg(offsets_out + mid) <= lo) bl = mid; else br = mid;
-    }
-    uint32_t x1[L], y1[L], x2[L], y2[L], den[L], run[L];
-    F::set_one(run);
-    // walk state = the bucket owning the NEXT slot (one ahead of the slot being computed)
-    uint32_t b = bl, out_end = __ldg(offsets_out + b + 1), out_beg = __ldg(offsets_out + b), in_beg = __ldg(offsets_in + b),
-             in_end = __ldg(offsets_in + b + 1);
-    // ---- forward: running product of the denominators, parked in the x-half of each output slot (x coordinates only)
-    uint32_t k = in_beg + 2 * (lo - out_beg);
-    bool has2 = k + 1 < in_end;
-    for (uint32_t p = lo; p < hi; p++) {
-        uint32_t kn = 0;
-        bool has2n = false;
-        if (p + 1 < hi) {
-            while (p + 1 >= out_end) {
-                b++;
-                out_beg = out_end;
-                out_end = __ldg(offsets_out + b + 1);
-                in_beg = __ldg(offsets_in + b);
-                in_end = __ldg(offsets_in + b + 1);
-            }
-            kn = in_beg + 2 * (p + 1 - out_beg);
-            has2n = kn + 1 < in_end;
-        }
-        if (has2) {
-            pair_load_x<F, FIRST>(x1, bases, src, k);
-            pair_load_x<F, FIRST>(x2, bases, src, k + 1);
-            if (limbs_is_zero<L>(x1) || limbs_is_zero<L>(x2) || limbs_eq<L>(x1, x2)) {   // rare: identity operand / equal x
-                pair_load_point<F, FIRST>(x1, y1, bases, src, k);
-                pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
-                const int kind = pair_classify<F>(den, x1, y1, x2, y2, true);
-                if (kind >= PAIR_ADD) F::mul(run, run, den);
-            } else {
-                F::sub(den, x2, x1);
-                F::mul(run, run, den);
-            }
-        }
-        store_limbs<L>(out + (size_t)p * (2 * L), run);
-        k = kn;
-        has2 = has2n;
-    }
-    uint32_t inv[L];
-    F::inv(inv, run);
-    // ---- backward: peel the inverses off and write the sums; the walk state now sits on the bucket of slot hi-1
-    k = in_beg + 2 * (hi - 1 - out_beg);
-    has2 = k + 1 < in_end;
-    for (uint32_t p = hi; p-- > lo;) {
-        uint32_t kn = 0;
-        bool has2n = false;
-        if (p > lo) {
-            while (p - 1 < out_beg) {
-                b--;
-                out_end = out_beg;
-                out_beg = __ldg(offsets_out + b);
-                in_beg = __ldg(offsets_in + b);
-                in_end = __ldg(offsets_in + b + 1);
-            }
-            kn = in_beg + 2 * (p - 1 - out_beg);
-            has2n = kn + 1 < in_end;
-        }
-        pair_load_point<F, FIRST>(x1, y1, bases, src, k);
-        if (has2) pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
-        const int kind = pair_classify<F>(den, x1, y1, x2, y2, has2);
-        uint32_t *o = out + (size_t)p * (2 * L);
-        if (kind >= PAIR_ADD) {
-            uint32_t dinv[L], lam[L], t3[L];
-            if (p > lo) { load_limbs<L>(t3, out + (size_t)(p - 1) * (2 * L)); F::mul(dinv, inv, t3); }   // inv * prefix_{p-1} = 1/den
-            else limbs_copy<L>(dinv, inv);
-            F::mul(inv, inv, den);
-            if (kind == PAIR_ADD) {
-                F::sub(lam, y2, y1);
-            } else {                      // doubling: slope = 3 x^2 / (2 y)
-                F::sqr(lam, x1);
-                F::dbl(t3, lam);
-                F::add(lam, lam, t3);
-                limbs_copy<L>(x2, x1);
-            }
-            F::mul(lam, lam, dinv);
-            F::sqr(t3, lam);
-            F::sub(t3, t3, x1);
-            F::sub(t3, t3, x2);           // x3
-            F::sub(x2, x1, t3);
-            F::mul(x2, lam, x2);
-            F::sub(x2, x2, y1);           // y3 = lam (x1 - x3) - y1
-            store_limbs<L>(o, t3);
-            store_limbs<L>(o + L, x2);
-        } else if (kind == PAIR_PASS1) {
-            store_limbs<L>(o, x1);
-            store_limbs<L>(o + L, y1);
-        } else if (kind == PAIR_PASS2) {
-            store_limbs<L>(o, x2);
-            store_limbs<L>(o + L, y2);
-        } else {
-            F::set_zero(x1);
-            store_limbs<L>(o, x1);
-            store_limbs<L>(o + L, x1);
-        }
-        k = kn;
-        has2 = has2n;
-    }
-}
-
-// bucket b = tail[t0] + head[t0+1] + ... + head[t1], t1 = task holding the bucket's last entry.
-// small spans: one thread per task boundary; long spans (heavy buckets): one block per bucket.
-static constexpr uint32_t kFixupSmall = 16;
-template <class C>
-__global__ void __launch_bounds__(128) msm_fixup_small_kernel(const uint32_t *__restrict__ offsets, uint32_t T, const uint32_t *__restrict__ head,
-                                                              const uint32_t *__restrict__ tail, const uint32_t *__restrict__ tail_bucket,
-                                                              uint32_t num_tasks, uint32_t *__restrict__ buckets) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_tasks) return;
-    const uint32_t b = tail_bucket[t];
-    if (b == kNoBucket) return;
-    const uint32_t t1 = (__ldg(offsets + b + 1) - 1 - __ldg(offsets)) / T;
-    if (t1 - t > kFixupSmall) return;
-    typename E::B acc, x;
-    load_xyzz<L>(acc, tail + (size_t)t * (4 * L));
-    for (uint32_t k = t + 1; k <= t1; k++) {
-        load_xyzz<L>(x, head + (size_t)k * (4 * L));
-        E::xyzz_add(acc, x);
-    }
-    store_xyzz<L>(buckets + (size_t)b * (4 * L), acc);
-}
-template <class C>
-__global__ void __launch_bounds__(128) msm_fixup_big_kernel(const uint32_t *__restrict__ offsets, uint32_t T, const uint32_t *__restrict__ head,
-                                                            const uint32_t *__restrict__ tail, const uint32_t *__restrict__ tail_bucket,
-                                                            uint32_t num_tasks, uint32_t *__restrict__ buckets) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    extern __shared__ uint32_t sm[];
-    const uint32_t t = blockIdx.x;
-    if (t >= num_tasks) return;
-    const uint32_t b = tail_bucket[t];
-    if (b == kNoBucket) return;
-    const uint32_t t1 = (__ldg(offsets + b + 1) - 1 - __ldg(offsets)) / T;
-    if (t1 - t <= kFixupSmall) return;
-    typename E::B acc, x;
-    E::xyzz_set_zero(acc);
-    if (threadIdx.x == 0) load_xyzz<L>(acc, tail + (size_t)t * (4 * L));
-    for (uint32_t k = t + 1 + threadIdx.x; k <= t1; k += blockDim.x) {
-        load_xyzz<L>(x, head + (size_t)k * (4 * L));
-        E::xyzz_add(acc, x);
-    }
-    store_xyzz<L>(sm + threadIdx.x * (4 * L), acc);
-    __syncthreads();
-    for (uint32_t s2 = blockDim.x >> 1; s2 > 0; s2 >>= 1) {
-        if (threadIdx.x < s2) {
-            load_xyzz<L>(acc, sm + threadIdx.x * (4 * L));
-            load_xyzz<L>(x, sm + (threadIdx.x + s2) * (4 * L));
-            E::xyzz_add(acc, x);
-            store_xyzz<L>(sm + threadIdx.x * (4 * L), acc);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        load_xyzz<L>(acc, sm);
-        store_xyzz<L>(buckets + (size_t)b * (4 * L), acc);
-    }
-}
-
-template <int L> __device__ __forceinline__ void load_xyzz(Xyzz<L> &b, const uint32_t *p) {
-    load_limbs<L>(b.x, p);
-    load_limbs<L>(b.y, p + L);
-    load_limbs<L>(b.zz, p + 2 * L);
-    load_limbs<L>(b.zzz, p + 3 * L);
-}
-template <int L> __device__ __forceinline__ void store_xyzz(uint32_t *p, const Xyzz<L> &b) {
-    store_limbs<L>(p, b.x);
-    store_limbs<L>(p + L, b.y);
-    store_limbs<L>(p + 2 * L, b.zz);
-    store_limbs<L>(p + 3 * L, b.zzz);
-}
-
-// ------------------------------------------------------------------------------------------------
-// bucket reduction.  Window w needs S_w = sum_j (j+1) * B_w[j]  (:478-484).  Thread t of a window takes buckets
-// [t*m, (t+1)*m): running sum gives  sum_l (l+1)*B[t*m+l]  and the chunk total R_t; adding (t*m) * R_t (double-and-add)
-// makes its contribution complete.  partial index = window * chunks_stride + t.
-// ------------------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const uint32_t *__restrict__ buckets, MsmGeom g, int log_m,
-                                                                uint32_t chunks_per_window, uint32_t *__restrict__ partials) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t w = tid / chunks_per_window, t = tid % chunks_per_window;
-    if (w >= (uint32_t)g.W) return;
-    const uint32_t nbw = (w == (uint32_t)g.W - 1) ? g.nb_top : g.nb;
-    const uint32_t m = 1u << log_m;
-    typename E::B run, sum;
-    E::xyzz_set_zero(run);
-    E::xyzz_set_zero(sum);
-    const uint32_t lo = t * m;
-    if (lo < nbw) {
-        const uint32_t hi = min(lo + m, nbw);
-        const uint32_t *base = buckets + ((size_t)w * g.nb) * (4 * L);
-        for (uint32_t j = hi; j-- > lo;) {
-            typename E::B b;
-            load_xyzz<L>(b, base + (size_t)j * (4 * L));
-            E::xyzz_add(run, b);
-            E::xyzz_add(sum, run);
-        }
-        // sum += lo * run
-        if (lo != 0 && !E::xyzz_is_zero(run)) {
-            typename E::B acc;
-            E::xyzz_set_zero(acc);
-            for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-                if (!E::xyzz_is_zero(acc)) E::xyzz_dbl(acc);
-                if ((lo >> bit) & 1) E::xyzz_add(acc, run);
-            }
-            E::xyzz_add(sum, acc);
-        }
-    }
-    store_xyzz<L>(partials + ((size_t)w * chunks_per_window + t) * (4 * L), sum);
-}
-
-// one block per window: strided sums then a shared-memory tree; result -> window_sums[w]
-template <class C>
-__global__ void __launch_bounds__(128) msm_sum_partials_kernel(const uint32_t *__restrict__ partials, uint32_t chunks_per_window,
-                                                               uint32_t *__restrict__ window_sums) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    extern __shared__ uint32_t sm[];
-    const uint32_t w = blockIdx.x;
-    typename E::B acc;
-    E::xyzz_set_zero(acc);
-    for (uint32_t t = threadIdx.x; t < chunks_per_window; t += blockDim.x) {
-        typename E::B b;
-        load_xyzz<L>(b, partials + ((size_t)w * chunks_per_window + t) * (4 * L));
-        E::xyzz_add(acc, b);
-    }
-    store_xyzz<L>(sm + threadIdx.x * (4 * L), acc);
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            typename E::B a, b;
-            load_xyzz<L>(a, sm + threadIdx.x * (4 * L));
-            load_xyzz<L>(b, sm + (threadIdx.x + s) * (4 * L));
-            E::xyzz_add(a, b);
-            store_xyzz<L>(sm + threadIdx.x * (4 * L), a);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        typename E::B a;
-        load_xyzz<L>(a, sm);
-        store_xyzz<L>(window_sums + (size_t)w * (4 * L), a);
-    }
-}
-
-// total = sum_w 2^(c*w) * S_w by Horner (:489-502); Jacobian result (x, y, z) -> out (3L words)
-template <class C> __global__ void msm_window_combine_kernel(const uint32_t *__restrict__ window_sums, int W, int c, uint32_t *__restrict__ out) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    typename E::J total;
-    E::jac_set_zero(total);
-    for (int w = W - 1; w >= 0; w--) {
-        typename E::B b;
-        typename E::J j;
-        load_xyzz<L>(b, window_sums + (size_t)w * (4 * L));
-        E::xyzz_to_jac(j, b);
-        E::jac_add(total, j);  // Projective += &Bucket (bucket.rs:345-359)
-        if (w > 0)
-            for (int d = 0; d < c; d++) E::jac_dbl(total);
-    }
-    store_limbs<L>(out, total.x);
-    store_limbs<L>(out + L, total.y);
-    store_limbs<L>(out + 2 * L, total.z);
-}
-
-// sum of k Jacobian points (multi-GPU gather reduce), one thread
-template <class C> __global__ void jac_sum_kernel(const uint32_t *__restrict__ pts, size_t k, uint32_t *__restrict__ out) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    typename E::J total;
-    E::jac_set_zero(total);
-    for (size_t i = 0; i < k; i++) {
-        typename E::J j;
-        load_limbs<L>(j.x, pts + i * 3 * L);
-        load_limbs<L>(j.y, pts + i * 3 * L + L);
-        load_limbs<L>(j.z, pts + i * 3 * L + 2 * L);
-        E::jac_add(total, j);
-    }
-    if (E::jac_is_zero(total)) E::jac_set_zero(total);
-    store_limbs<L>(out, total.x);
-    store_limbs<L>(out + L, total.y);
-    store_limbs<L>(out + 2 * L, total.z);
-}
-template <class C> __global__ void jac_to_affine_kernel(const uint32_t *__restrict__ pts, size_t k, uint32_t *__restrict__ out) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k) return;
-    typename E::J j;
-    load_limbs<L>(j.x, pts + i * 3 * L);
-    load_limbs<L>(j.y, pts + i * 3 * L + L);
-    load_limbs<L>(j.z, pts + i * 3 * L + 2 * L);
-    uint32_t ax[L], ay[L];
-    E::jac_to_affine(ax, ay, j);
-    store_limbs<L>(out + i * 2 * L, ax);
-    store_limbs<L>(out + i * 2 * L + L, ay);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Pair-add, second generation: warp-interleaved slots + asynchronous operand staging.
-//   * a WARP owns 32*batch consecutive output slots and lane l takes slots l, l+32, l+64, ... — every Montgomery-trick chain is
-//     still private to one thread, but the 32 lanes of a load/store touch 32 consecutive slots (coalesced streaming for the
-//     levels >= 2 and for the parked prefix products);
-//   * the operands of the NEXT slot are fetched with cp.async (LDGSTS) into a per-thread shared-memory strip while the current
-//     slot's multiplications run, so the random 96-byte gathers of level 1 no longer stall the integer pipe and cost no registers;
-//   * slot -> input-pair mapping comes from `pairmap` (msm_pairmap_kernel), not from a per-thread bucket walk.
-// Same arithmetic, same degenerate-pair handling and same output layout as msm_pair_add_kernel.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// per-thread strip: element e, 16-byte chunk j of thread t lives at uint4 index (e*(L/4) + j)*128 + t (conflict-free)
-template <int L> __device__ __forceinline__ void strip_fetch(uint32_t sbase, int e, const uint32_t *g) {
-#pragma unroll
-    for (int j = 0; j < L / 4; j++) cp_async16(sbase + ((uint32_t)((e * (L / 4) + j) * 128 + threadIdx.x) << 4), g + 4 * j);
-}
-template <int L> __device__ __forceinline__ void strip_read(uint32_t *r, const uint4 *sm, int e) {
-#pragma unroll
-    for (int j = 0; j < L / 4; j++) {
-        const uint4 v = sm[(e * (L / 4) + j) * 128 + threadIdx.x];
-        r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
-    }
-}
-
-// pairmap[p] = (index of the first input entry of output slot p) | (the slot has a second entry) << 31.
-// One block per 1024 consecutive slots: two threads locate the first and last bucket of the block's slot range, the bucket
-// offsets in between are staged in shared memory and every slot finds its bucket by a short binary search there (any bucket
 // size distribution costs the same; a run of > 2048 buckets inside one block — mostly empty ones — falls back to global loads).
 __global__ void __launch_bounds__(256) msm_pairmap_kernel(const uint32_t *__restrict__ offsets_in, const uint32_t *__restrict__ offsets_out,
                                                           uint32_t nb, uint32_t *__restrict__ pairmap) {
@@ -771,157 +159,6 @@ __global__ void __launch_bounds__(256) msm_pairmap_kernel(const uint32_t *__rest
         pairmap[p] = k | ((k + 1 < in_end) ? 0x80000000u : 0u);
     }
 }
-
-template <class C, bool FIRST, int MINB>
-__global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
-                                                                const uint32_t *__restrict__ pairmap, const uint32_t *__restrict__ offsets_out,
-                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out) {
-    using F = typename C::F;
-    constexpr int L = F::L;
-    extern __shared__ uint4 strip[];
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(strip);
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t M = __ldg(offsets_out + nb);
-    const uint64_t w_lo = (uint64_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * 32 * batch;
-    if (w_lo + lane >= M) return;
-    const uint32_t w_hi = (uint32_t)min((uint64_t)M, w_lo + (uint64_t)32 * batch);
-    const uint32_t p0 = (uint32_t)w_lo + lane;
-    const uint32_t cnt = (w_hi - p0 + 31) >> 5;   // slots p0 + 32*i, i < cnt
-    // address of the point behind input entry `k` (FIRST: through the sorted index, e = index | sign << 31)
-    auto point = [&](uint32_t k, uint32_t e) -> const uint32_t * {
-        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
-    };
-    uint32_t x1[L], y1[L], x2[L], y2[L], den[L], run[L];
-    // software pipeline over the slots of this lane: (m, e1, e2) describe a slot (pairmap word and, for FIRST, the two sorted
-    // entries); *_c = slot being computed, *_n = next slot (operands in flight), m_nn = pairmap word two slots ahead
-    uint32_t m_c, m_n = 0, m_nn = 0, e1_c = 0, e2_c = 0, e1_n = 0, e2_n = 0;
-
-    // ---------------- forward: running product of the denominators (x coordinates only), parked in the x-half of the slots
-    m_c = __ldg(pairmap + p0);
-    if (FIRST) { e1_c = __ldg(src + (m_c & 0x7fffffffu)); if (m_c >> 31) e2_c = __ldg(src + (m_c & 0x7fffffffu) + 1); }
-    // (forward uses strip elements {0,2} for even slots and {1,3} for odd ones: a true double buffer)
-    if (m_c >> 31) { strip_fetch<L>(sbase, 0, point(m_c & 0x7fffffffu, e1_c)); strip_fetch<L>(sbase, 2, point((m_c & 0x7fffffffu) + 1, e2_c)); }
-    cp_async_commit();
-    if (cnt > 1) {
-        m_n = __ldg(pairmap + p0 + 32);
-        if (FIRST) { e1_n = __ldg(src + (m_n & 0x7fffffffu)); if (m_n >> 31) e2_n = __ldg(src + (m_n & 0x7fffffffu) + 1); }
-    }
-    if (cnt > 2) m_nn = __ldg(pairmap + p0 + 64);
-    F::set_one(run);
-    for (uint32_t i = 0; i < cnt; i++) {
-        cp_async_wait_all();
-        const bool has2 = (m_c >> 31) != 0;
-        const int eb = (int)(i & 1);
-        if (has2) { strip_read<L>(x1, strip, eb); strip_read<L>(x2, strip, 2 + eb); }
-        if (i + 1 < cnt && (m_n >> 31)) {
-            strip_fetch<L>(sbase, 1 - eb, point(m_n & 0x7fffffffu, e1_n));
-            strip_fetch<L>(sbase, 3 - eb, point((m_n & 0x7fffffffu) + 1, e2_n));
-        }
-        cp_async_commit();
-        uint32_t e1_nn = 0, e2_nn = 0, m_n3 = 0;
-        if (FIRST && i + 2 < cnt) { e1_nn = __ldg(src + (m_nn & 0x7fffffffu)); if (m_nn >> 31) e2_nn = __ldg(src + (m_nn & 0x7fffffffu) + 1); }
-        if (i + 3 < cnt) m_n3 = __ldg(pairmap + p0 + 32 * (i + 3));
-        if (has2) {
-            if (limbs_is_zero<L>(x1) || limbs_is_zero<L>(x2) || limbs_eq<L>(x1, x2)) {   // rare: identity operand / equal x
-                const uint32_t k = m_c & 0x7fffffffu;
-                pair_load_point<F, FIRST>(x1, y1, bases, src, k);
-                pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
-                const int kind = pair_classify<F>(den, x1, y1, x2, y2, true);
-                if (kind >= PAIR_ADD) F::mul(run, run, den);
-            } else {
-                F::sub(den, x2, x1);
-                F::mul(run, run, den);
-            }
-        }
-        store_limbs<L>(out + (size_t)(p0 + 32 * i) * (2 * L), run);
-        m_c = m_n; e1_c = e1_n; e2_c = e2_n;
-        m_n = m_nn; e1_n = e1_nn; e2_n = e2_nn;
-        m_nn = m_n3;
-    }
-    uint32_t inv[L];
-    F::inv(inv, run);
-
-    // ---------------- backward: peel the inverses off and write the sums; strip elements 0..3 = x1, y1, x2, y2, 4 = prefix
-    auto fetch_bwd = [&](uint32_t m, uint32_t e1, uint32_t e2, uint32_t i) {   // operands of slot i and the prefix parked in slot i-1
-        const uint32_t k = m & 0x7fffffffu;
-        const uint32_t *a = point(k, e1);
-        strip_fetch<L>(sbase, 0, a);
-        strip_fetch<L>(sbase, 1, a + L);
-        if (m >> 31) {
-            const uint32_t *b = point(k + 1, e2);
-            strip_fetch<L>(sbase, 2, b);
-            strip_fetch<L>(sbase, 3, b + L);
-        }
-        if (i > 0) strip_fetch<L>(sbase, 4, out + (size_t)(p0 + 32 * (i - 1)) * (2 * L));
-    };
-    m_c = __ldg(pairmap + p0 + 32 * (cnt - 1));
-    e1_c = e2_c = e1_n = e2_n = 0;
-    m_n = m_nn = 0;
-    if (FIRST) { e1_c = __ldg(src + (m_c & 0x7fffffffu)); if (m_c >> 31) e2_c = __ldg(src + (m_c & 0x7fffffffu) + 1); }
-    fetch_bwd(m_c, e1_c, e2_c, cnt - 1);
-    cp_async_commit();
-    if (cnt > 1) {
-        m_n = __ldg(pairmap + p0 + 32 * (cnt - 2));
-        if (FIRST) { e1_n = __ldg(src + (m_n & 0x7fffffffu)); if (m_n >> 31) e2_n = __ldg(src + (m_n & 0x7fffffffu) + 1); }
-    }
-    if (cnt > 2) m_nn = __ldg(pairmap + p0 + 32 * (cnt - 3));
-    for (uint32_t i = cnt; i-- > 0;) {
-        cp_async_wait_all();
-        const bool has2 = (m_c >> 31) != 0;
-        uint32_t dinv[L];
-        strip_read<L>(x1, strip, 0);
-        strip_read<L>(y1, strip, 1);
-        if (has2) { strip_read<L>(x2, strip, 2); strip_read<L>(y2, strip, 3); }
-        if (i > 0) { strip_read<L>(dinv, strip, 4); F::mul(dinv, inv, dinv); }   // inv * prefix_{i-1} = 1/den_i
-        else limbs_copy<L>(dinv, inv);
-        if (FIRST) {
-            F::cneg(y1, y1, (e1_c >> 31) != 0);
-            if (has2) F::cneg(y2, y2, (e2_c >> 31) != 0);
-        }
-        if (i > 0) fetch_bwd(m_n, e1_n, e2_n, i - 1);
-        cp_async_commit();
-        uint32_t e1_nn = 0, e2_nn = 0, m_n3 = 0;
-        if (FIRST && i >= 2) { e1_nn = __ldg(src + (m_nn & 0x7fffffffu)); if (m_nn >> 31) e2_nn = __ldg(src + (m_nn & 0x7fffffffu) + 1); }
-        if (i >= 3) m_n3 = __ldg(pairmap + p0 + 32 * (i - 3));
-        const int kind = pair_classify<F>(den, x1, y1, x2, y2, has2);
-        uint32_t *o = out + (size_t)(p0 + 32 * i) * (2 * L);
-        if (kind >= PAIR_ADD) {
-            uint32_t lam[L], t3[L];
-            F::mul(inv, inv, den);
-            if (kind == PAIR_ADD) {
-                F::sub(lam, y2, y1);
-            } else {                      // doubling: slope = 3 x^2 / (2 y)
-                F::sqr(lam, x1);
-                F::dbl(t3, lam);
-                F::add(lam, lam, t3);
-                limbs_copy<L>(x2, x1);
-            }
-            F::mul(lam, lam, dinv);
-            F::sqr(t3, lam);
-            F::sub(t3, t3, x1);
-            F::sub(t3, t3, x2);           // x3
-            F::sub(x2, x1, t3);
-            F::mul(x2, lam, x2);
-            F::sub(x2, x2, y1);           // y3 = lam (x1 - x3) - y1
-            store_limbs<L>(o, t3);
-            store_limbs<L>(o + L, x2);
-        } else if (kind == PAIR_PASS1) {
-            store_limbs<L>(o, x1);
-            store_limbs<L>(o + L, y1);
-        } else if (kind == PAIR_PASS2) {
-            store_limbs<L>(o, x2);
-            store_limbs<L>(o + L, y2);
-        } else {
-            F::set_zero(x1);
-            store_limbs<L>(o, x1);
-            store_limbs<L>(o + L, x1);
-        }
-        m_c = m_n; e1_c = e1_n; e2_c = e2_n;
-        m_n = m_nn; e1_n = e1_nn; e2_n = e2_nn;
-        m_nn = m_n3;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
@@ -984,22 +221,6 @@ int msm_auto_window(size_t n, int scalar_bits) {
         if (t < best) { best = t; best_c = c; }
     }
     return best_c;
-}
-
-// buckets[b] += extra[b]  (chunked paths: every chunk after the first accumulates into `extra`)
-template <class C>
-__global__ void __launch_bounds__(128) msm_merge_kernel(uint32_t *__restrict__ buckets, const uint32_t *__restrict__ extra, uint32_t total_buckets) {
-    using F = typename C::F;
-    using E = Ec<F>;
-    constexpr int L = F::L;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total_buckets) return;
-    typename E::B x, y;
-    load_xyzz<L>(y, extra + (size_t)b * (4 * L));
-    if (E::xyzz_is_zero(y)) return;
-    load_xyzz<L>(x, buckets + (size_t)b * (4 * L));
-    E::xyzz_add(x, y);
-    store_xyzz<L>(buckets + (size_t)b * (4 * L), x);
 }
 
 static int scalar_kind_bits(int kind, int field_bits) {
@@ -1155,9 +376,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
     int accumulate(const uint32_t *pts, const uint32_t *sorted_idx, const uint32_t *offs, size_t nbk, size_t entries, uint32_t *dst) {
         if (!entries) return 0;
         // balanced tasks: T entries per thread such that the grid is a whole number of waves (no tail), T <= 512
-        int blocks_per_sm = 3;
-        if (sorted_idx) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, msm_accumulate_kernel<C, false>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, msm_accumulate_kernel<C, true>, 128, 0);
+        const int blocks_per_sm = MsmAccLaunch<C>::occupancy(sorted_idx == nullptr);
         const double wave = (double)sm_count() * std::max(blocks_per_sm, 1) * 128.0;
         const double per_thread = (double)entries / wave;
         uint32_t T;
@@ -1173,16 +392,9 @@ template <class C> struct MsmSession final : MsmSessionBase {
         if (int rc = arena.alloc(&tail, (size_t)num_tasks * 4 * L * 4)) return rc;
         if (int rc = arena.alloc(&head_bucket, (size_t)num_tasks * 4)) return rc;
         if (int rc = arena.alloc(&tail_bucket, (size_t)num_tasks * 4)) return rc;
-        const unsigned grid = (num_tasks + 127) / 128;
-        if (sorted_idx)
-            msm_accumulate_kernel<C, false><<<grid, 128, 0, st>>>(pts, sorted_idx, offs, (uint32_t)nbk, T, dst, head, tail, head_bucket, tail_bucket, num_tasks);
-        else
-            msm_accumulate_kernel<C, true><<<grid, 128, 0, st>>>(pts, nullptr, offs, (uint32_t)nbk, T, dst, head, tail, head_bucket, tail_bucket, num_tasks);
-        AB_LAUNCHED();
-        msm_fixup_small_kernel<C><<<grid, 128, 0, st>>>(offs, T, head, tail, tail_bucket, num_tasks, dst);
-        AB_LAUNCHED();
-        msm_fixup_big_kernel<C><<<num_tasks, 128, 128 * 4 * L * 4, st>>>(offs, T, head, tail, tail_bucket, num_tasks, dst);
-        AB_LAUNCHED();
+        if (int rc = MsmAccLaunch<C>::accumulate(sorted_idx == nullptr, pts, sorted_idx, offs, (uint32_t)nbk, T, num_tasks, dst, head, tail, head_bucket,
+                                                 tail_bucket, st))
+            return rc;
         arena.release(head);
         arena.release(tail);
         arena.release(head_bucket);
@@ -1217,30 +429,14 @@ template <class C> struct MsmSession final : MsmSessionBase {
             msm_halve_counts_kernel<<<(unsigned)((nbg + 255) / 256), 256, 0, st>>>(cur_offsets, (uint32_t)nbg, counts);
             AB_LAUNCHED();
             if (int rc = scan(counts, nbg, off2)) return rc;
+            uint32_t *pairmap = nullptr;
             if (variant == 2) {
-                uint32_t *pairmap = nullptr;
                 if (int rc = arena.alloc(&pairmap, out_cap * 4)) return rc;
                 msm_pairmap_kernel<<<(unsigned)((out_cap + 1023) / 1024), 256, 0, st>>>(cur_offsets, off2, (uint32_t)nbg, pairmap);
                 AB_LAUNCHED();
-                const size_t warps = (out_cap + (size_t)32 * batch - 1) / ((size_t)32 * batch);
-                const unsigned pg = (unsigned)((warps + 3) / 4);
-                const size_t smem = (size_t)5 * (L / 4) * 128 * 16;
-                if (lv == 0) {
-                    AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, true, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bas, cur_src, pairmap, off2, (uint32_t)nbg, batch, pts);
-                } else {
-                    AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, false, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bas, cur_src, pairmap, off2, (uint32_t)nbg, batch, pts);
-                }
-                AB_LAUNCHED();
-                arena.release(pairmap);
-            } else {
-                const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);
-                const unsigned pg = (nthreads + 127) / 128;
-                if (lv == 0) msm_pair_add_kernel<C, true, C::PAIR_MINB><<<pg, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nbg, batch, pts, nthreads);
-                else msm_pair_add_kernel<C, false, C::PAIR_MINB><<<pg, 128, 0, st>>>(bas, cur_src, cur_offsets, off2, (uint32_t)nbg, batch, pts, nthreads);
-                AB_LAUNCHED();
             }
+            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts, st)) return rc;
+            arena.release(pairmap);
             // the level before the previous one is no longer read
             arena.release(lvl_pts[lv & 1]);
             arena.release(lvl_off[lv & 1]);
@@ -1276,11 +472,8 @@ template <class C> struct MsmSession final : MsmSessionBase {
         }
         AB_CUDA(cudaEventRecord(e[0], st));
         AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
-        const unsigned dblocks = (unsigned)((nk + 255) / 256);
-        if (nk) {
-            msm_digits_kernel<C, 0><<<dblocks, 256, 0, st>>>(d_scalars, kind, nk, g, 0, g.W, counts, nullptr);
-            AB_LAUNCHED();
-        }
+        if (nk)
+            if (int rc = MsmAccLaunch<C>::digits(0, d_scalars, kind, nk, g, 0, g.W, counts, nullptr, st)) return rc;
         AB_CUDA(cudaEventRecord(e[1], st));
         if (int rc = scan(counts, nb_total, offsets)) return rc;
         AB_CUDA(cudaMemcpyAsync(cursor, offsets, nb_total * 4, cudaMemcpyDeviceToDevice, st));
@@ -1290,10 +483,8 @@ template <class C> struct MsmSession final : MsmSessionBase {
         if (nk) {
             const size_t front_bytes = (size_t)g.nb * 32;
             const int group = (int)std::max<size_t>(1, ((size_t)48 << 20) / front_bytes);
-            for (int w0 = 0; w0 < g.W; w0 += group) {
-                msm_digits_kernel<C, 1><<<dblocks, 256, 0, st>>>(d_scalars, kind, nk, g, w0, std::min(g.W, w0 + group), cursor, sorted);
-                AB_LAUNCHED();
-            }
+            for (int w0 = 0; w0 < g.W; w0 += group)
+                if (int rc = MsmAccLaunch<C>::digits(1, d_scalars, kind, nk, g, w0, std::min(g.W, w0 + group), cursor, sorted, st)) return rc;
         }
         AB_CUDA(cudaEventRecord(e[3], st));
         AB_CUDA(cudaMemsetAsync(target, 0, nb_total * 4 * L * 4, st));
@@ -1329,8 +520,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
             }
         }
         if (chunks_done > 0) {
-            msm_merge_kernel<C><<<(unsigned)((nb_total + 127) / 128), 128, 0, st>>>(buckets, extra, (uint32_t)nb_total);
-            AB_LAUNCHED();
+            if (int rc = MsmAccLaunch<C>::merge(buckets, extra, (uint32_t)nb_total, st)) return rc;
         }
         AB_CUDA(cudaEventRecord(e[4], st));
         chunks_done++;
@@ -1351,14 +541,9 @@ template <class C> struct MsmSession final : MsmSessionBase {
         uint32_t *partials = nullptr, *window_sums = nullptr;
         if (int rc = arena.alloc(&partials, (size_t)g.W * chunks * 4 * L * 4)) return rc;
         if (int rc = arena.alloc(&window_sums, (size_t)g.W * 4 * L * 4)) return rc;
-        const unsigned rthreads = (unsigned)g.W * chunks;
-        msm_bucket_reduce_kernel<C><<<(rthreads + 127) / 128, 128, 0, st>>>(buckets, g, log_m, chunks, partials);
-        AB_LAUNCHED();
-        msm_sum_partials_kernel<C><<<g.W, 128, 128 * 4 * L * 4, st>>>(partials, chunks, window_sums);
-        AB_LAUNCHED();
+        if (int rc = MsmRedLaunch<C>::reduce(buckets, g, log_m, chunks, partials, window_sums, st)) return rc;
         AB_CUDA(cudaEventRecord(e_red, st));
-        msm_window_combine_kernel<C><<<1, 32, 0, st>>>(window_sums, g.W, g.c, d_out);
-        AB_LAUNCHED();
+        if (int rc = MsmRedLaunch<C>::combine(window_sums, g.W, g.c, d_out, st)) return rc;
         AB_CUDA(cudaEventRecord(e_end, st));
         return 0;
     }
@@ -1468,10 +653,6 @@ int msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucke
     return 0;
 }
 
-template <class C> static void launch_sum(bool to_affine, const uint32_t *d_in, size_t k, uint32_t *d_out, cudaStream_t st) {
-    if (to_affine) jac_to_affine_kernel<C><<<(unsigned)((k + 31) / 32), 32, 0, st>>>(d_in, k, d_out);
-    else jac_sum_kernel<C><<<1, 32, 0, st>>>(d_in, k, d_out);
-}
 int g1_sum_dispatch(int curve, const uint64_t *pts_host, size_t k, uint64_t *out_host, bool to_affine) {
     const int L = msm_coord_words(curve);
     if (!L) { set_last_error("unknown curve id"); return B200_EINVAL; }
@@ -1484,13 +665,15 @@ int g1_sum_dispatch(int curve, const uint64_t *pts_host, size_t k, uint64_t *out
     if (int rc = arena.alloc(&d_in, std::max<size_t>(in_words, 1) * 4)) return rc;
     if (int rc = arena.alloc(&d_out, std::max<size_t>(out_words, 1) * 4)) return rc;
     AB_CUDA(cudaMemcpyAsync(d_in, pts_host, in_words * 4, cudaMemcpyHostToDevice, st));
-    if (curve == B200_CURVE_BLS12_381) launch_sum<CurveBls>(to_affine, d_in, k, d_out, st);
-    else if (curve == B200_CURVE_BN254) launch_sum<CurveBn>(to_affine, d_in, k, d_out, st);
-    else launch_sum<CurveBlsG2>(to_affine, d_in, k, d_out, st);
-    AB_LAUNCHED();
+    int rc;
+    if (curve == B200_CURVE_BLS12_381) rc = MsmRedLaunch<CurveBls>::sum_or_affine(to_affine, d_in, k, d_out, st);
+    else if (curve == B200_CURVE_BN254) rc = MsmRedLaunch<CurveBn>::sum_or_affine(to_affine, d_in, k, d_out, st);
+    else rc = MsmRedLaunch<CurveBlsG2>::sum_or_affine(to_affine, d_in, k, d_out, st);
+    if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(out_host, d_out, out_words * 4, cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
 }  // namespace ab200
+

@@ -1,0 +1,378 @@
+// msm_k_pair.cuh — batched-affine pair-add kernels (both generations) and their launcher.
+#pragma once
+#include "msm_common.cuh"
+
+namespace ab200 {
+
+template <class F, bool FIRST>
+__device__ __forceinline__ void pair_load_point(uint32_t *x, uint32_t *y, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
+                                                uint32_t k) {
+    constexpr int L = F::L;
+    if (FIRST) {
+        const uint32_t e = __ldg(src + k);
+        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
+        load_limbs_nc<L>(x, bp);
+        load_limbs_nc<L>(y, bp + L);
+        F::cneg(y, y, (e >> 31) != 0);   // -(0,0) stays (0,0)
+    } else {
+        const uint32_t *bp = src + (size_t)k * (2 * L);
+        load_limbs_nc<L>(x, bp);
+        load_limbs_nc<L>(y, bp + L);
+    }
+}
+// x coordinate only (the forward pass needs y only for the rare degenerate pairs)
+template <class F, bool FIRST>
+__device__ __forceinline__ void pair_load_x(uint32_t *x, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src, uint32_t k) {
+    constexpr int L = F::L;
+    const uint32_t *bp = FIRST ? bases + (size_t)(__ldg(src + k) & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
+    load_limbs_nc<L>(x, bp);
+}
+
+enum { PAIR_PASS1 = 0, PAIR_PASS2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
+// classify (P1, P2) and produce the denominator of the slope (ONE for the degenerate kinds)
+template <class F> __device__ __forceinline__ int pair_classify(uint32_t *den, const uint32_t *x1, const uint32_t *y1, const uint32_t *x2,
+                                                                const uint32_t *y2, bool has2) {
+    constexpr int L = F::L;
+    const bool z1 = limbs_is_zero<L>(x1) && limbs_is_zero<L>(y1);
+    const bool z2 = !has2 || (limbs_is_zero<L>(x2) && limbs_is_zero<L>(y2));
+    F::set_one(den);
+    if (z2) return PAIR_PASS1;            // also covers "both identity" (P1 = (0,0) passes through)
+    if (z1) return PAIR_PASS2;
+    if (limbs_eq<L>(x1, x2)) {
+        if (limbs_eq<L>(y1, y2) && !limbs_is_zero<L>(y1)) { F::dbl(den, y1); return PAIR_DBL; }
+        return PAIR_INF;
+    }
+    F::sub(den, x2, x1);
+    return PAIR_ADD;
+}
+
+// Latency hiding in this kernel is left to occupancy (128 registers -> 16 warps per SM).  Measured alternatives @2^26,
+// accumulation phase with 4 levels: plain loads 285 ms; next-slot operands held in registers (198 regs, 8 warps/SM) 329 ms;
+// prefetch.global.L2 of the next slot's operands (fetches whole 128-byte lines for 96-byte points) 346 ms.
+template <class C, bool FIRST, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_pair_add_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
+                                                           const uint32_t *__restrict__ offsets_in, const uint32_t *__restrict__ offsets_out,
+                                                           uint32_t total_buckets, uint32_t batch, uint32_t *__restrict__ out,
+                                                           uint32_t num_threads) {
+    using F = typename C::F;
+    constexpr int L = F::L;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_threads) return;
+    const uint32_t M = __ldg(offsets_out + total_buckets);
+    const uint64_t lo64 = (uint64_t)t * batch;
+    if (lo64 >= M) return;
+    const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min((uint64_t)M, lo64 + batch);
+    uint32_t bl = 0, br = total_buckets;   // last b with offsets_out[b] <= lo
+    while (br - bl > 1) {
+        uint32_t mid = bl + ((br - bl) >> 1);
+        if (__ldg(offsets_out + mid) <= lo) bl = mid; else br = mid;
+    }
+    uint32_t x1[L], y1[L], x2[L], y2[L], den[L], run[L];
+    F::set_one(run);
+    // walk state = the bucket owning the NEXT slot (one ahead of the slot being computed)
+    uint32_t b = bl, out_end = __ldg(offsets_out + b + 1), out_beg = __ldg(offsets_out + b), in_beg = __ldg(offsets_in + b),
+             in_end = __ldg(offsets_in + b + 1);
+    // ---- forward: running product of the denominators, parked in the x-half of each output slot (x coordinates only)
+    uint32_t k = in_beg + 2 * (lo - out_beg);
+    bool has2 = k + 1 < in_end;
+    for (uint32_t p = lo; p < hi; p++) {
+        uint32_t kn = 0;
+        bool has2n = false;
+        if (p + 1 < hi) {
+            while (p + 1 >= out_end) {
+                b++;
+                out_beg = out_end;
+                out_end = __ldg(offsets_out + b + 1);
+                in_beg = __ldg(offsets_in + b);
+                in_end = __ldg(offsets_in + b + 1);
+            }
+            kn = in_beg + 2 * (p + 1 - out_beg);
+            has2n = kn + 1 < in_end;
+        }
+        if (has2) {
+            pair_load_x<F, FIRST>(x1, bases, src, k);
+            pair_load_x<F, FIRST>(x2, bases, src, k + 1);
+            if (limbs_is_zero<L>(x1) || limbs_is_zero<L>(x2) || limbs_eq<L>(x1, x2)) {   // rare: identity operand / equal x
+                pair_load_point<F, FIRST>(x1, y1, bases, src, k);
+                pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
+                const int kind = pair_classify<F>(den, x1, y1, x2, y2, true);
+                if (kind >= PAIR_ADD) F::mul(run, run, den);
+            } else {
+                F::sub(den, x2, x1);
+                F::mul(run, run, den);
+            }
+        }
+        store_limbs<L>(out + (size_t)p * (2 * L), run);
+        k = kn;
+        has2 = has2n;
+    }
+    uint32_t inv[L];
+    F::inv(inv, run);
+    // ---- backward: peel the inverses off and write the sums; the walk state now sits on the bucket of slot hi-1
+    k = in_beg + 2 * (hi - 1 - out_beg);
+    has2 = k + 1 < in_end;
+    for (uint32_t p = hi; p-- > lo;) {
+        uint32_t kn = 0;
+        bool has2n = false;
+        if (p > lo) {
+            while (p - 1 < out_beg) {
+                b--;
+                out_end = out_beg;
+                out_beg = __ldg(offsets_out + b);
+                in_beg = __ldg(offsets_in + b);
+                in_end = __ldg(offsets_in + b + 1);
+            }
+            kn = in_beg + 2 * (p - 1 - out_beg);
+            has2n = kn + 1 < in_end;
+        }
+        pair_load_point<F, FIRST>(x1, y1, bases, src, k);
+        if (has2) pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
+        const int kind = pair_classify<F>(den, x1, y1, x2, y2, has2);
+        uint32_t *o = out + (size_t)p * (2 * L);
+        if (kind >= PAIR_ADD) {
+            uint32_t dinv[L], lam[L], t3[L];
+            if (p > lo) { load_limbs<L>(t3, out + (size_t)(p - 1) * (2 * L)); F::mul(dinv, inv, t3); }   // inv * prefix_{p-1} = 1/den
+            else limbs_copy<L>(dinv, inv);
+            F::mul(inv, inv, den);
+            if (kind == PAIR_ADD) {
+                F::sub(lam, y2, y1);
+            } else {                      // doubling: slope = 3 x^2 / (2 y)
+                F::sqr(lam, x1);
+                F::dbl(t3, lam);
+                F::add(lam, lam, t3);
+                limbs_copy<L>(x2, x1);
+            }
+            F::mul(lam, lam, dinv);
+            F::sqr(t3, lam);
+            F::sub(t3, t3, x1);
+            F::sub(t3, t3, x2);           // x3
+            F::sub(x2, x1, t3);
+            F::mul(x2, lam, x2);
+            F::sub(x2, x2, y1);           // y3 = lam (x1 - x3) - y1
+            store_limbs<L>(o, t3);
+            store_limbs<L>(o + L, x2);
+        } else if (kind == PAIR_PASS1) {
+            store_limbs<L>(o, x1);
+            store_limbs<L>(o + L, y1);
+        } else if (kind == PAIR_PASS2) {
+            store_limbs<L>(o, x2);
+            store_limbs<L>(o + L, y2);
+        } else {
+            F::set_zero(x1);
+            store_limbs<L>(o, x1);
+            store_limbs<L>(o + L, x1);
+        }
+        k = kn;
+        has2 = has2n;
+    }
+}
+
+// bucket b = tail[t0] + head[t0+1] + ... + head[t1], t1 = task holding the bucket's last entry.
+// ------------------------------------------------------------------------------------------------
+// Pair-add, second generation: warp-interleaved slots + asynchronous operand staging.
+//   * a WARP owns 32*batch consecutive output slots and lane l takes slots l, l+32, l+64, ... — every Montgomery-trick chain is
+//     still private to one thread, but the 32 lanes of a load/store touch 32 consecutive slots (coalesced streaming for the
+//     levels >= 2 and for the parked prefix products);
+//   * the operands of the NEXT slot are fetched with cp.async (LDGSTS) into a per-thread shared-memory strip while the current
+//     slot's multiplications run, so the random 96-byte gathers of level 1 no longer stall the integer pipe and cost no registers;
+//   * slot -> input-pair mapping comes from `pairmap` (msm_pairmap_kernel), not from a per-thread bucket walk.
+// Same arithmetic, same degenerate-pair handling and same output layout as msm_pair_add_kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// per-thread strip: element e, 16-byte chunk j of thread t lives at uint4 index (e*(L/4) + j)*128 + t (conflict-free)
+template <int L> __device__ __forceinline__ void strip_fetch(uint32_t sbase, int e, const uint32_t *g) {
+#pragma unroll
+    for (int j = 0; j < L / 4; j++) cp_async16(sbase + ((uint32_t)((e * (L / 4) + j) * 128 + threadIdx.x) << 4), g + 4 * j);
+}
+template <int L> __device__ __forceinline__ void strip_read(uint32_t *r, const uint4 *sm, int e) {
+#pragma unroll
+    for (int j = 0; j < L / 4; j++) {
+        const uint4 v = sm[(e * (L / 4) + j) * 128 + threadIdx.x];
+        r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+    }
+}
+
+// pairmap[p] = (index of the first input entry of output slot p) | (the slot has a second entry) << 31.
+// One block per 1024 consecutive slots: two threads locate the first and last bucket of the block's slot range, the bucket
+// offsets in between are staged in shared memory and every slot finds its bucket by a short binary search there (any bucket
+template <class C, bool FIRST, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
+                                                                const uint32_t *__restrict__ pairmap, const uint32_t *__restrict__ offsets_out,
+                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out) {
+    using F = typename C::F;
+    constexpr int L = F::L;
+    extern __shared__ uint4 strip[];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(strip);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t M = __ldg(offsets_out + nb);
+    const uint64_t w_lo = (uint64_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * 32 * batch;
+    if (w_lo + lane >= M) return;
+    const uint32_t w_hi = (uint32_t)min((uint64_t)M, w_lo + (uint64_t)32 * batch);
+    const uint32_t p0 = (uint32_t)w_lo + lane;
+    const uint32_t cnt = (w_hi - p0 + 31) >> 5;   // slots p0 + 32*i, i < cnt
+    // address of the point behind input entry `k` (FIRST: through the sorted index, e = index | sign << 31)
+    auto point = [&](uint32_t k, uint32_t e) -> const uint32_t * {
+        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
+    };
+    uint32_t x1[L], y1[L], x2[L], y2[L], den[L], run[L];
+    // software pipeline over the slots of this lane: (m, e1, e2) describe a slot (pairmap word and, for FIRST, the two sorted
+    // entries); *_c = slot being computed, *_n = next slot (operands in flight), m_nn = pairmap word two slots ahead
+    uint32_t m_c, m_n = 0, m_nn = 0, e1_c = 0, e2_c = 0, e1_n = 0, e2_n = 0;
+
+    // ---------------- forward: running product of the denominators (x coordinates only), parked in the x-half of the slots
+    m_c = __ldg(pairmap + p0);
+    if (FIRST) { e1_c = __ldg(src + (m_c & 0x7fffffffu)); if (m_c >> 31) e2_c = __ldg(src + (m_c & 0x7fffffffu) + 1); }
+    // (forward uses strip elements {0,2} for even slots and {1,3} for odd ones: a true double buffer)
+    if (m_c >> 31) { strip_fetch<L>(sbase, 0, point(m_c & 0x7fffffffu, e1_c)); strip_fetch<L>(sbase, 2, point((m_c & 0x7fffffffu) + 1, e2_c)); }
+    cp_async_commit();
+    if (cnt > 1) {
+        m_n = __ldg(pairmap + p0 + 32);
+        if (FIRST) { e1_n = __ldg(src + (m_n & 0x7fffffffu)); if (m_n >> 31) e2_n = __ldg(src + (m_n & 0x7fffffffu) + 1); }
+    }
+    if (cnt > 2) m_nn = __ldg(pairmap + p0 + 64);
+    F::set_one(run);
+    for (uint32_t i = 0; i < cnt; i++) {
+        cp_async_wait_all();
+        const bool has2 = (m_c >> 31) != 0;
+        const int eb = (int)(i & 1);
+        if (has2) { strip_read<L>(x1, strip, eb); strip_read<L>(x2, strip, 2 + eb); }
+        if (i + 1 < cnt && (m_n >> 31)) {
+            strip_fetch<L>(sbase, 1 - eb, point(m_n & 0x7fffffffu, e1_n));
+            strip_fetch<L>(sbase, 3 - eb, point((m_n & 0x7fffffffu) + 1, e2_n));
+        }
+        cp_async_commit();
+        uint32_t e1_nn = 0, e2_nn = 0, m_n3 = 0;
+        if (FIRST && i + 2 < cnt) { e1_nn = __ldg(src + (m_nn & 0x7fffffffu)); if (m_nn >> 31) e2_nn = __ldg(src + (m_nn & 0x7fffffffu) + 1); }
+        if (i + 3 < cnt) m_n3 = __ldg(pairmap + p0 + 32 * (i + 3));
+        if (has2) {
+            if (limbs_is_zero<L>(x1) || limbs_is_zero<L>(x2) || limbs_eq<L>(x1, x2)) {   // rare: identity operand / equal x
+                const uint32_t k = m_c & 0x7fffffffu;
+                pair_load_point<F, FIRST>(x1, y1, bases, src, k);
+                pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
+                const int kind = pair_classify<F>(den, x1, y1, x2, y2, true);
+                if (kind >= PAIR_ADD) F::mul(run, run, den);
+            } else {
+                F::sub(den, x2, x1);
+                F::mul(run, run, den);
+            }
+        }
+        store_limbs<L>(out + (size_t)(p0 + 32 * i) * (2 * L), run);
+        m_c = m_n; e1_c = e1_n; e2_c = e2_n;
+        m_n = m_nn; e1_n = e1_nn; e2_n = e2_nn;
+        m_nn = m_n3;
+    }
+    uint32_t inv[L];
+    F::inv(inv, run);
+
+    // ---------------- backward: peel the inverses off and write the sums; strip elements 0..3 = x1, y1, x2, y2, 4 = prefix
+    auto fetch_bwd = [&](uint32_t m, uint32_t e1, uint32_t e2, uint32_t i) {   // operands of slot i and the prefix parked in slot i-1
+        const uint32_t k = m & 0x7fffffffu;
+        const uint32_t *a = point(k, e1);
+        strip_fetch<L>(sbase, 0, a);
+        strip_fetch<L>(sbase, 1, a + L);
+        if (m >> 31) {
+            const uint32_t *b = point(k + 1, e2);
+            strip_fetch<L>(sbase, 2, b);
+            strip_fetch<L>(sbase, 3, b + L);
+        }
+        if (i > 0) strip_fetch<L>(sbase, 4, out + (size_t)(p0 + 32 * (i - 1)) * (2 * L));
+    };
+    m_c = __ldg(pairmap + p0 + 32 * (cnt - 1));
+    e1_c = e2_c = e1_n = e2_n = 0;
+    m_n = m_nn = 0;
+    if (FIRST) { e1_c = __ldg(src + (m_c & 0x7fffffffu)); if (m_c >> 31) e2_c = __ldg(src + (m_c & 0x7fffffffu) + 1); }
+    fetch_bwd(m_c, e1_c, e2_c, cnt - 1);
+    cp_async_commit();
+    if (cnt > 1) {
+        m_n = __ldg(pairmap + p0 + 32 * (cnt - 2));
+        if (FIRST) { e1_n = __ldg(src + (m_n & 0x7fffffffu)); if (m_n >> 31) e2_n = __ldg(src + (m_n & 0x7fffffffu) + 1); }
+    }
+    if (cnt > 2) m_nn = __ldg(pairmap + p0 + 32 * (cnt - 3));
+    for (uint32_t i = cnt; i-- > 0;) {
+        cp_async_wait_all();
+        const bool has2 = (m_c >> 31) != 0;
+        uint32_t dinv[L];
+        strip_read<L>(x1, strip, 0);
+        strip_read<L>(y1, strip, 1);
+        if (has2) { strip_read<L>(x2, strip, 2); strip_read<L>(y2, strip, 3); }
+        if (i > 0) { strip_read<L>(dinv, strip, 4); F::mul(dinv, inv, dinv); }   // inv * prefix_{i-1} = 1/den_i
+        else limbs_copy<L>(dinv, inv);
+        if (FIRST) {
+            F::cneg(y1, y1, (e1_c >> 31) != 0);
+            if (has2) F::cneg(y2, y2, (e2_c >> 31) != 0);
+        }
+        if (i > 0) fetch_bwd(m_n, e1_n, e2_n, i - 1);
+        cp_async_commit();
+        uint32_t e1_nn = 0, e2_nn = 0, m_n3 = 0;
+        if (FIRST && i >= 2) { e1_nn = __ldg(src + (m_nn & 0x7fffffffu)); if (m_nn >> 31) e2_nn = __ldg(src + (m_nn & 0x7fffffffu) + 1); }
+        if (i >= 3) m_n3 = __ldg(pairmap + p0 + 32 * (i - 3));
+        const int kind = pair_classify<F>(den, x1, y1, x2, y2, has2);
+        uint32_t *o = out + (size_t)(p0 + 32 * i) * (2 * L);
+        if (kind >= PAIR_ADD) {
+            uint32_t lam[L], t3[L];
+            F::mul(inv, inv, den);
+            if (kind == PAIR_ADD) {
+                F::sub(lam, y2, y1);
+            } else {                      // doubling: slope = 3 x^2 / (2 y)
+                F::sqr(lam, x1);
+                F::dbl(t3, lam);
+                F::add(lam, lam, t3);
+                limbs_copy<L>(x2, x1);
+            }
+            F::mul(lam, lam, dinv);
+            F::sqr(t3, lam);
+            F::sub(t3, t3, x1);
+            F::sub(t3, t3, x2);           // x3
+            F::sub(x2, x1, t3);
+            F::mul(x2, lam, x2);
+            F::sub(x2, x2, y1);           // y3 = lam (x1 - x3) - y1
+            store_limbs<L>(o, t3);
+            store_limbs<L>(o + L, x2);
+        } else if (kind == PAIR_PASS1) {
+            store_limbs<L>(o, x1);
+            store_limbs<L>(o + L, y1);
+        } else if (kind == PAIR_PASS2) {
+            store_limbs<L>(o, x2);
+            store_limbs<L>(o + L, y2);
+        } else {
+            F::set_zero(x1);
+            store_limbs<L>(o, x1);
+            store_limbs<L>(o + L, x1);
+        }
+        m_c = m_n; e1_c = e1_n; e2_c = e2_n;
+        m_n = m_nn; e1_n = e1_nn; e2_n = e2_nn;
+        m_nn = m_n3;
+    }
+}
+
+template <class C>
+int MsmPairLaunch<C>::run(int variant, bool first, const uint32_t *bases, const uint32_t *src, const uint32_t *offsets_in, const uint32_t *offsets_out,
+                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, cudaStream_t st) {
+    constexpr int L = C::F::L;
+    if (variant == 2) {
+        const size_t warps = (out_cap + (size_t)32 * batch - 1) / ((size_t)32 * batch);
+        const unsigned pg = (unsigned)((warps + 3) / 4);
+        const size_t smem = (size_t)5 * (L / 4) * 128 * 16;
+        if (first) {
+            AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, true, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out);
+        } else {
+            AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, false, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out);
+        }
+    } else {
+        const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);
+        const unsigned pg = (nthreads + 127) / 128;
+        if (first) msm_pair_add_kernel<C, true, C::PAIR_MINB><<<pg, 128, 0, st>>>(bases, src, offsets_in, offsets_out, nbg, batch, out, nthreads);
+        else msm_pair_add_kernel<C, false, C::PAIR_MINB><<<pg, 128, 0, st>>>(bases, src, offsets_in, offsets_out, nbg, batch, out, nthreads);
+    }
+    AB_LAUNCHED();
+    return 0;
+}
+
+}  // namespace ab200

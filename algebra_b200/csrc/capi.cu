@@ -485,28 +485,45 @@ int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const 
     return 0;
 }
 
-int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const uint64_t *coset_offset) {
+// host-buffer transform: H2D of the `len_in` given elements only (the zero padding of `fft_in_place`'s resize is produced on the
+// device), transform, D2H of all 2^log_n results
+int b200_ntt_fr_padded(int field, const uint64_t *in, size_t len_in, uint64_t *out, uint32_t log_n, int inverse, const uint64_t *coset_offset) {
     { int irc = ensure_device_init(); if (irc) return irc; }
-    if (!data) { set_last_error("null data pointer"); return B200_EINVAL; }
+    if (!out || (len_in && !in)) { set_last_error("null data pointer"); return B200_EINVAL; }
     if (field != B200_FIELD_BLS12_381_FR && field != B200_FIELD_BN254_FR) { set_last_error("unknown scalar field id"); return B200_EINVAL; }
     if (log_n > (uint32_t)(field == B200_FIELD_BLS12_381_FR ? 32 : 28)) {
         set_last_error("log_n exceeds TWO_ADICITY (Radix2EvaluationDomain::new would return None)");
         return B200_ETOOLARGE;
     }
-    const size_t bytes = ((size_t)32) << log_n;
-    cudaStream_t st = 0;
+    const size_t n = (size_t)1 << log_n, bytes = n * 32;
+    if (len_in > n) len_in = n;   // coeffs.resize(self.size(), ..) truncates (radix2/mod.rs:144)
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    CtxLease lease;
+    if (int rc = lease.acquire(dev)) return rc;
+    DeviceCtx &c = *lease.c;
     void *d = nullptr;
-    AB_CUDA(cudaMallocAsync(&d, bytes, st));
-    AB_CUDA(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, st));
-    int rc = ntt_dispatch(field, d, log_n, inverse, coset_offset, st);
-    if (rc == 0) {
-        cudaError_t e = cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H", __FILE__, __LINE__);
-    }
-    cudaFreeAsync(d, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    AB_CUDA(cudaMallocAsync(&d, bytes, c.st));
+    int rc = 0;
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, c.st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c.copy_st, ev, 0);
+    if (e != cudaSuccess) rc = cuda_fail(e, "event setup", __FILE__, __LINE__);
+    if (!rc) rc = h2d(c, d, in, len_in * 32);                       // pinned: async; pageable: staged through the pinned ring
+    if (!rc) { e = cudaEventRecord(ev, c.copy_st); if (e == cudaSuccess) e = cudaStreamWaitEvent(c.st, ev, 0); if (e != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__); }
+    if (!rc && len_in < n) { e = cudaMemsetAsync((char *)d + len_in * 32, 0, (n - len_in) * 32, c.st); if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__); }
+    if (!rc) rc = ntt_dispatch(field, d, log_n, inverse, coset_offset, c.st);
+    if (!rc) { e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, c.st); if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync D2H", __FILE__, __LINE__); }
+    cudaStreamSynchronize(c.copy_st);
+    cudaFreeAsync(d, c.st);
+    e = cudaStreamSynchronize(c.st);
+    if (!rc && e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    if (ev) cudaEventDestroy(ev);
     return rc;
+}
+int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const uint64_t *coset_offset) {
+    return b200_ntt_fr_padded(field, data, log_n <= 40 ? (size_t)1 << log_n : 0, data, log_n, inverse, coset_offset);
 }
 int b200_clear_cache(void) {
     int rc = ntt_clear_cache();

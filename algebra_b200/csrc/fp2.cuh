@@ -14,6 +14,14 @@ template <class P> struct Fp2 {
     using B = Fp<P>;
     static constexpr int LB = P::L;
     static constexpr int L = 2 * P::L;
+    // Base-field multiplication as a CALL on the device: an inlined Fp2 multiplication is three ~600-instruction Montgomery
+    // bodies, and a G2 point addition has 14 of them — far beyond the instruction cache (the G1 kernels already show
+    // `no_instruction` stalls at a third of that size) and minutes of compile time per kernel.  One shared body per kernel instead.
+#ifdef __CUDA_ARCH__
+    static __device__ __noinline__ void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
+#else
+    static inline void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
+#endif
     static AB_HD void add(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::add(r, a, b); B::add(r + LB, a + LB, b + LB); }
     static AB_HD void sub(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::sub(r, a, b); B::sub(r + LB, a + LB, b + LB); }
     static AB_HD void dbl(uint32_t *r, const uint32_t *a) { B::dbl(r, a); B::dbl(r + LB, a + LB); }
@@ -22,11 +30,11 @@ template <class P> struct Fp2 {
     // (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u      [3 base multiplications]
     static AB_HD void mul(uint32_t *r, const uint32_t *a, const uint32_t *b) {
         uint32_t v0[LB], v1[LB], sa[LB], sb[LB];
-        B::mul(v0, a, b);
-        B::mul(v1, a + LB, b + LB);
+        bmul(v0, a, b);
+        bmul(v1, a + LB, b + LB);
         B::add(sa, a, a + LB);
         B::add(sb, b, b + LB);
-        B::mul(sa, sa, sb);
+        bmul(sa, sa, sb);
         B::sub(sa, sa, v0);
         B::sub(r + LB, sa, v1);
         B::sub(r, v0, v1);
@@ -36,20 +44,20 @@ template <class P> struct Fp2 {
         uint32_t s[LB], d[LB], m[LB];
         B::add(s, a, a + LB);
         B::sub(d, a, a + LB);
-        B::mul(m, a, a + LB);
-        B::mul(r, s, d);
+        bmul(m, a, a + LB);
+        bmul(r, s, d);
         B::dbl(r + LB, m);
     }
     static AB_HD void set_one(uint32_t *r) { B::set_one(r); B::set_zero(r + LB); }
     static AB_HD void set_zero(uint32_t *r) { B::set_zero(r); B::set_zero(r + LB); }
     static AB_HD void inv(uint32_t *r, const uint32_t *a) {
         uint32_t n[LB], t[LB];
-        B::sqr(n, a);
-        B::sqr(t, a + LB);
+        bmul(n, a, a);
+        bmul(t, a + LB, a + LB);
         B::add(n, n, t);       // norm = c0^2 + c1^2
         B::inv(n, n);
-        B::mul(r, a, n);
-        B::mul(t, a + LB, n);
+        bmul(r, a, n);
+        bmul(t, a + LB, n);
         B::neg(r + LB, t);
     }
 };

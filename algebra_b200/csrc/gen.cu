@@ -42,17 +42,33 @@ template <class P> __global__ void gen_scalars_kernel(uint64_t seed, size_t n, u
     store_limbs<8>(out + i * 8, v);
 }
 
-// table[w*256 + d] = (d * 256^w) * G, affine Montgomery (d = 0 -> (0,0))
-template <class P> __global__ void gen_table_kernel(uint32_t *table) {
-    using E = Ec<Fp<P>>;
+// generator traits: coordinate-field operations class + the generator's affine coordinates (Montgomery words)
+template <class P> struct GenG1 {
     using F = Fp<P>;
-    constexpr int L = P::L;
+    static __device__ __forceinline__ void generator(uint32_t *x, uint32_t *y) {
+#pragma unroll
+        for (int i = 0; i < P::L; i++) { x[i] = P::GEN_X(i); y[i] = P::GEN_Y(i); }
+    }
+};
+struct GenBlsG2 {
+    using F = Fp2<BlsFq>;
+    static __device__ __forceinline__ void generator(uint32_t *x, uint32_t *y) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) { x[i] = BlsG2Gen::GEN_X(i); y[i] = BlsG2Gen::GEN_Y(i); }
+    }
+};
+
+// table[w*256 + d] = (d * 256^w) * G, affine Montgomery (d = 0 -> (0,0))
+template <class G> __global__ void gen_table_kernel(uint32_t *table) {
+    using F = typename G::F;
+    using E = Ec<F>;
+    constexpr int L = F::L;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 8 * 256) return;
     int w = t >> 8, d = t & 255;
     typename E::J base, acc;
-#pragma unroll
-    for (int i = 0; i < L; i++) { base.x[i] = P::GEN_X(i); base.y[i] = P::GEN_Y(i); base.z[i] = P::ONE(i); }
+    G::generator(base.x, base.y);
+    F::set_one(base.z);
     for (int k = 0; k < 8 * w; k++) E::jac_dbl(base);
     E::jac_set_zero(acc);
     for (int bit = 7; bit >= 0; bit--) {
@@ -63,14 +79,13 @@ template <class P> __global__ void gen_table_kernel(uint32_t *table) {
     E::jac_to_affine(ax, ay, acc);
     store_limbs<L>(table + (size_t)t * 2 * L, ax);
     store_limbs<L>(table + (size_t)t * 2 * L + L, ay);
-    (void)sizeof(F);
 }
 
-template <class P> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64_t seed, size_t n, const uint32_t *__restrict__ table,
+template <class G> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64_t seed, size_t n, const uint32_t *__restrict__ table,
                                                                          uint32_t *__restrict__ bases, uint64_t *__restrict__ bvals) {
-    using E = Ec<Fp<P>>;
-    using F = Fp<P>;
-    constexpr int L = P::L;
+    using F = typename G::F;
+    using E = Ec<F>;
+    constexpr int L = F::L;
     size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kGenBatch;
     if (i0 >= n) return;
     typename E::B pts[kGenBatch];
@@ -223,8 +238,8 @@ template <class P> __global__ void __launch_bounds__(64) normalize_batch_kernel(
 static std::mutex g_table_mutex;
 static std::map<std::pair<int, int>, uint32_t *> g_tables;
 
-template <class P> static int gen_bases_run(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, cudaStream_t st) {
-    constexpr int L = P::L;
+template <class G> static int gen_bases_run(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, cudaStream_t st) {
+    constexpr int L = G::F::L;
     int dev = 0;
     AB_CUDA(cudaGetDevice(&dev));
     uint32_t *table = nullptr;
@@ -234,14 +249,14 @@ template <class P> static int gen_bases_run(int curve, uint64_t seed, size_t n, 
         auto it = g_tables.find(key);
         if (it == g_tables.end()) {
             AB_CUDA(cudaMalloc(&table, (size_t)8 * 256 * 2 * L * 4));
-            gen_table_kernel<P><<<(8 * 256 + 63) / 64, 64, 0, st>>>(table);
+            gen_table_kernel<G><<<(8 * 256 + 63) / 64, 64, 0, st>>>(table);
             AB_LAUNCHED();
             AB_CUDA(cudaStreamSynchronize(st));
             g_tables[key] = table;
         } else table = it->second;
     }
     size_t threads = (n + kGenBatch - 1) / kGenBatch;
-    gen_bases_kernel<P><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(seed, n, table, (uint32_t *)d_bases, (uint64_t *)d_b);
+    gen_bases_kernel<G><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(seed, n, table, (uint32_t *)d_bases, (uint64_t *)d_b);
     AB_LAUNCHED();
     return 0;
 }
@@ -249,8 +264,9 @@ template <class P> static int gen_bases_run(int curve, uint64_t seed, size_t n, 
 int gen_bases_dispatch(int curve, uint64_t seed, size_t n, void *d_bases, void *d_b, cudaStream_t st) {
     if (!d_bases && n) { set_last_error("null pointer"); return B200_EINVAL; }
     if (n == 0) return 0;
-    if (curve == B200_CURVE_BLS12_381) return gen_bases_run<BlsFq>(curve, seed, n, d_bases, d_b, st);
-    if (curve == B200_CURVE_BN254) return gen_bases_run<BnFq>(curve, seed, n, d_bases, d_b, st);
+    if (curve == B200_CURVE_BLS12_381) return gen_bases_run<GenG1<BlsFq>>(curve, seed, n, d_bases, d_b, st);
+    if (curve == B200_CURVE_BN254) return gen_bases_run<GenG1<BnFq>>(curve, seed, n, d_bases, d_b, st);
+    if (curve == B200_CURVE_BLS12_381_G2) return gen_bases_run<GenBlsG2>(curve, seed, n, d_bases, d_b, st);
     set_last_error("unknown curve id");
     return B200_EINVAL;
 }

@@ -167,11 +167,16 @@ __global__ void __launch_bounds__(256) msm_pairmap_kernel(const uint32_t *__rest
 struct EnvKnobs {
     int pair_variant = 2;                 // 1 = thread-contiguous batches, 2 = warp-interleaved + cp.async staging
     double level_budget_bytes = 24e9;     // scratch allowed for the affine level arrays (window groups are sized to fit)
+    int shared_inv = 1;                   // one field inversion per block (Montgomery's trick across the block) instead of per thread
+    int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
     EnvKnobs() {
         if (const char *e = getenv("B200_MSM_PAIR_VARIANT")) pair_variant = atoi(e) == 1 ? 1 : 2;
         if (const char *e = getenv("B200_MSM_LEVEL_BUDGET_GB")) { double v = atof(e); if (v > 0.01) level_budget_bytes = v * 1e9; }
+        if (const char *e = getenv("B200_MSM_SHARED_INV")) shared_inv = atoi(e) != 0;
+        min_batch = shared_inv ? 96 : 256;   // overhead per addition: 590/(4*batch) multiplications shared, 570/batch per thread
+        if (const char *e = getenv("B200_MSM_MIN_BATCH")) min_batch = std::max(8, atoi(e));
         if (const char *e = getenv("B200_MSM_FORCE_CHUNKS")) force_chunks = atoi(e);
         if (const char *e = getenv("B200_L2_FETCH_GRANULARITY")) l2_fetch_granularity = atoi(e);
     }
@@ -419,10 +424,11 @@ template <class C> struct MsmSession final : MsmSessionBase {
             // threads so that no SM idles through a partial last wave; in automatic mode a level that cannot give every
             // resident thread >= 256 slots is left to the XYZZ kernel instead (measured: thin levels are slower).
             const double per_lane = (double)out_cap / lanes_per_wave;
-            if (!forced && per_lane < 256.0) break;
+            const double min_batch = (double)env_knobs().min_batch;
+            if (!forced && per_lane < min_batch) break;
             const double waves = std::max(1.0, std::ceil(per_lane / 1024.0));
             uint32_t batch = (uint32_t)std::ceil((double)out_cap / (waves * lanes_per_wave));
-            batch = std::min(1024u, std::max(forced ? 8u : 256u, batch));
+            batch = std::min(1024u, std::max(forced ? 8u : (uint32_t)min_batch, batch));
             uint32_t *pts = nullptr, *off2 = nullptr;
             if (int rc = arena.alloc(&pts, out_cap * 2 * L * 4)) return rc;
             if (int rc = arena.alloc(&off2, (nbg + 1) * 4)) return rc;
@@ -435,7 +441,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 msm_pairmap_kernel<<<(unsigned)((out_cap + 1023) / 1024), 256, 0, st>>>(cur_offsets, off2, (uint32_t)nbg, pairmap);
                 AB_LAUNCHED();
             }
-            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts, st)) return rc;
+            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts, env_knobs().shared_inv, st)) return rc;
             arena.release(pairmap);
             // the level before the previous one is no longer read
             arena.release(lvl_pts[lv & 1]);
@@ -497,7 +503,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 if (C::AUTO_LEVELS)
                     for (double l = (double)nk / (double)g.nb; l >= 16.0 && levels < 4; l *= 0.5) levels++;
                 // the first level must be able to give every resident thread a batch of >= 256 additions
-                if ((double)nk * g.W * 0.5 / ((double)sm_count() * 512.0) < 256.0) levels = 0;
+                if ((double)nk * g.W * 0.5 / ((double)sm_count() * 512.0) < (double)env_knobs().min_batch) levels = 0;
             }
             if (levels == 0) {
                 if (int rc = accumulate(bas, sorted, offsets, nb_total, nk * (size_t)g.W, target)) return rc;
@@ -506,8 +512,8 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 // levels alive at a time) must fit the scratch budget; groups are whole windows, balanced in size
                 const double per_window = ((double)nk * 0.5 + (double)g.nb * 0.5) * 2 * L * 4 * 1.5 + (double)nk * 0.5 * 4;
                 int gw = (int)std::floor(env_knobs().level_budget_bytes / per_window);
-                // ... and a group must give every resident thread a batch of >= 256 additions at level 1
-                const int gw_min = (int)std::ceil(256.0 * (double)sm_count() * 512.0 / ((double)nk * 0.5));
+                // ... and a group must give every resident thread a batch of >= min_batch additions at level 1
+                const int gw_min = (int)std::ceil((double)env_knobs().min_batch * (double)sm_count() * 512.0 / ((double)nk * 0.5));
                 gw = std::max(std::max(1, gw_min), std::min(g.W, gw));
                 gw = std::min(g.W, gw);
                 const int ngroups = (g.W + gw - 1) / gw;

@@ -46,6 +46,64 @@ template <class F> __device__ __forceinline__ int pair_classify(uint32_t *den, c
     return PAIR_ADD;
 }
 
+
+// Inverts the 128 per-thread products of a block with ONE field inversion (Montgomery's trick across the block): warp 0 takes
+// 4 products per lane, combines the 32 lane totals with a shuffle scan (prefix and suffix products), inverts the grand total and
+// peels the 128 inverses back out; every thread then picks up 1/run of its own product.  A per-thread inversion costs ~570
+// multiplications of issue time PER WARP; this costs ~590 per BLOCK, i.e. a quarter — which is what allows short batches.
+// `sm` holds 128 * L words (word i of thread t at sm[i * 128 + t]); all 128 threads of the block must call this.
+template <class F> __device__ __forceinline__ void shfl_limbs(uint32_t *r, const uint32_t *a, int src_lane) {
+#pragma unroll
+    for (int i = 0; i < F::L; i++) r[i] = __shfl_sync(0xffffffffu, a[i], src_lane);
+}
+template <class F> __device__ __noinline__ void block_inverse(uint32_t *inv, const uint32_t *run, uint32_t *sm) {
+    constexpr int L = F::L;
+    const int tid = threadIdx.x, lane = tid & 31;
+#pragma unroll
+    for (int i = 0; i < L; i++) sm[i * 128 + tid] = run[i];
+    __syncthreads();
+    if (tid < 32) {
+        auto rd = [&](uint32_t *v, int j) {
+#pragma unroll
+            for (int i = 0; i < L; i++) v[i] = sm[i * 128 + 4 * lane + j];
+        };
+        auto wr = [&](const uint32_t *v, int j) {
+#pragma unroll
+            for (int i = 0; i < L; i++) sm[i * 128 + 4 * lane + j] = v[i];
+        };
+        uint32_t v[L], a1[L], a2[L], a3[L], P[L], S[L], y[L];
+        rd(a1, 0); rd(v, 1); F::mul(a1, a1, v);      // a1 = v0 v1
+        rd(v, 2); F::mul(a2, a1, v);                 // a2 = v0 v1 v2
+        rd(v, 3); F::mul(a3, a2, v);                 // a3 = lane total
+        limbs_copy<L>(P, a3);
+        limbs_copy<L>(S, a3);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {           // inclusive prefix (P) and suffix (S) products over the lanes
+            shfl_limbs<F>(y, P, lane >= o ? lane - o : lane);
+            if (lane >= o) F::mul(P, P, y);
+            shfl_limbs<F>(y, S, lane + o < 32 ? lane + o : lane);
+            if (lane + o < 32) F::mul(S, S, y);
+        }
+        uint32_t I[L];
+        shfl_limbs<F>(y, P, 31);
+        F::inv(I, y);                                 // 1 / (product of all 128), computed redundantly by the 32 lanes
+        shfl_limbs<F>(y, P, lane ? lane - 1 : 0);
+        if (lane) F::mul(I, I, y);                    // ... times the products of the other lanes = 1 / a3
+        shfl_limbs<F>(y, S, lane < 31 ? lane + 1 : 31);
+        if (lane < 31) F::mul(I, I, y);
+        // peel: I = 1/(v0 v1 v2 v3)
+        rd(v, 3); F::mul(y, I, a2); F::mul(I, I, v); wr(y, 3);     // 1/v3 = I a2 ; I <- 1/(v0 v1 v2)
+        rd(v, 2); F::mul(y, I, a1); F::mul(I, I, v); wr(y, 2);     // 1/v2 = I a1 ; I <- 1/(v0 v1)
+        rd(v, 1); rd(a1, 0);
+        F::mul(y, I, a1); wr(y, 1);                                  // 1/v1 = I v0
+        F::mul(y, I, v); wr(y, 0);                                   // 1/v0 = I v1
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < L; i++) inv[i] = sm[i * 128 + tid];
+    __syncthreads();   // `sm` may be reused by the caller (the staging strips of the second-generation kernel)
+}
+
 // Latency hiding in this kernel is left to occupancy (128 registers -> 16 warps per SM).  Measured alternatives @2^26,
 // accumulation phase with 4 levels: plain loads 285 ms; next-slot operands held in registers (198 regs, 8 warps/SM) 329 ms;
 // prefetch.global.L2 of the next slot's operands (fetches whole 128-byte lines for 96-byte points) 346 ms.
@@ -53,15 +111,16 @@ template <class C, bool FIRST, int MINB>
 __global__ void __launch_bounds__(128, MINB) msm_pair_add_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
                                                            const uint32_t *__restrict__ offsets_in, const uint32_t *__restrict__ offsets_out,
                                                            uint32_t total_buckets, uint32_t batch, uint32_t *__restrict__ out,
-                                                           uint32_t num_threads) {
+                                                           uint32_t num_threads, int shared_inv) {
     using F = typename C::F;
     constexpr int L = F::L;
+    __shared__ uint32_t s_inv[128 * L];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_threads) return;
     const uint32_t M = __ldg(offsets_out + total_buckets);
     const uint64_t lo64 = (uint64_t)t * batch;
-    if (lo64 >= M) return;
-    const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min((uint64_t)M, lo64 + batch);
+    const bool active = t < num_threads && lo64 < M;
+    if (!active && !shared_inv) return;   // (with the block-shared inversion every thread has to reach the barriers)
+    const uint32_t lo = (uint32_t)min((uint64_t)M, lo64), hi = (uint32_t)min((uint64_t)M, lo64 + batch);
     uint32_t bl = 0, br = total_buckets;   // last b with offsets_out[b] <= lo
     while (br - bl > 1) {
         uint32_t mid = bl + ((br - bl) >> 1);
@@ -107,7 +166,8 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add_kernel(const uint32_t 
         has2 = has2n;
     }
     uint32_t inv[L];
-    F::inv(inv, run);
+    if (shared_inv) block_inverse<F>(inv, run, s_inv);
+    else F::inv(inv, run);
     // ---- backward: peel the inverses off and write the sums; the walk state now sits on the bucket of slot hi-1
     k = in_beg + 2 * (hi - 1 - out_beg);
     has2 = k + 1 < in_end;
@@ -203,7 +263,7 @@ template <int L> __device__ __forceinline__ void strip_read(uint32_t *r, const u
 template <class C, bool FIRST, int MINB>
 __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
                                                                 const uint32_t *__restrict__ pairmap, const uint32_t *__restrict__ offsets_out,
-                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out) {
+                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out, int shared_inv) {
     using F = typename C::F;
     constexpr int L = F::L;
     extern __shared__ uint4 strip[];
@@ -211,10 +271,11 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t M = __ldg(offsets_out + nb);
     const uint64_t w_lo = (uint64_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * 32 * batch;
-    if (w_lo + lane >= M) return;
+    const bool active = w_lo + lane < M;
+    if (!active && !shared_inv) return;   // (with the block-shared inversion every thread has to reach the barriers)
     const uint32_t w_hi = (uint32_t)min((uint64_t)M, w_lo + (uint64_t)32 * batch);
-    const uint32_t p0 = (uint32_t)w_lo + lane;
-    const uint32_t cnt = (w_hi - p0 + 31) >> 5;   // slots p0 + 32*i, i < cnt
+    const uint32_t p0 = active ? (uint32_t)w_lo + lane : 0;
+    const uint32_t cnt = active ? (w_hi - p0 + 31) >> 5 : 0;   // slots p0 + 32*i, i < cnt
     // address of the point behind input entry `k` (FIRST: through the sorted index, e = index | sign << 31)
     auto point = [&](uint32_t k, uint32_t e) -> const uint32_t * {
         return FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
@@ -225,6 +286,8 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
     uint32_t m_c, m_n = 0, m_nn = 0, e1_c = 0, e2_c = 0, e1_n = 0, e2_n = 0;
 
     // ---------------- forward: running product of the denominators (x coordinates only), parked in the x-half of the slots
+    F::set_one(run);
+    if (cnt) {
     m_c = __ldg(pairmap + p0);
     if (FIRST) { e1_c = __ldg(src + (m_c & 0x7fffffffu)); if (m_c >> 31) e2_c = __ldg(src + (m_c & 0x7fffffffu) + 1); }
     // (forward uses strip elements {0,2} for even slots and {1,3} for odd ones: a true double buffer)
@@ -235,7 +298,6 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
         if (FIRST) { e1_n = __ldg(src + (m_n & 0x7fffffffu)); if (m_n >> 31) e2_n = __ldg(src + (m_n & 0x7fffffffu) + 1); }
     }
     if (cnt > 2) m_nn = __ldg(pairmap + p0 + 64);
-    F::set_one(run);
     for (uint32_t i = 0; i < cnt; i++) {
         cp_async_wait_all();
         const bool has2 = (m_c >> 31) != 0;
@@ -266,8 +328,11 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
         m_n = m_nn; e1_n = e1_nn; e2_n = e2_nn;
         m_nn = m_n3;
     }
+    }
     uint32_t inv[L];
-    F::inv(inv, run);
+    if (shared_inv) block_inverse<F>(inv, run, reinterpret_cast<uint32_t *>(strip));   // (no copy is in flight here: the strips are free)
+    else F::inv(inv, run);
+    if (!cnt) return;
 
     // ---------------- backward: peel the inverses off and write the sums; strip elements 0..3 = x1, y1, x2, y2, 4 = prefix
     auto fetch_bwd = [&](uint32_t m, uint32_t e1, uint32_t e2, uint32_t i) {   // operands of slot i and the prefix parked in slot i-1
@@ -352,7 +417,7 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
 
 template <class C>
 int MsmPairLaunch<C>::run(int variant, bool first, const uint32_t *bases, const uint32_t *src, const uint32_t *offsets_in, const uint32_t *offsets_out,
-                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, cudaStream_t st) {
+                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, cudaStream_t st) {
     constexpr int L = C::F::L;
     if (variant == 2) {
         const size_t warps = (out_cap + (size_t)32 * batch - 1) / ((size_t)32 * batch);
@@ -360,16 +425,16 @@ int MsmPairLaunch<C>::run(int variant, bool first, const uint32_t *bases, const 
         const size_t smem = (size_t)5 * (L / 4) * 128 * 16;
         if (first) {
             AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, true, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out);
+            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv);
         } else {
             AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, false, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out);
+            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv);
         }
     } else {
         const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);
         const unsigned pg = (nthreads + 127) / 128;
-        if (first) msm_pair_add_kernel<C, true, C::PAIR_MINB><<<pg, 128, 0, st>>>(bases, src, offsets_in, offsets_out, nbg, batch, out, nthreads);
-        else msm_pair_add_kernel<C, false, C::PAIR_MINB><<<pg, 128, 0, st>>>(bases, src, offsets_in, offsets_out, nbg, batch, out, nthreads);
+        if (first) msm_pair_add_kernel<C, true, C::PAIR_MINB><<<pg, 128, 0, st>>>(bases, src, offsets_in, offsets_out, nbg, batch, out, nthreads, shared_inv);
+        else msm_pair_add_kernel<C, false, C::PAIR_MINB><<<pg, 128, 0, st>>>(bases, src, offsets_in, offsets_out, nbg, batch, out, nthreads, shared_inv);
     }
     AB_LAUNCHED();
     return 0;

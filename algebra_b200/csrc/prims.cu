@@ -31,6 +31,30 @@ template <class P> __global__ void fp_op_kernel(int op, const uint32_t *a, const
     store_limbs<L>(out + i * L, r);
 }
 
+// same surface for the quadratic extension (field id 4 = BLS12-381 Fq2): ops 0 mul 1 add 2 sub 3 square 4 double 5 neg 8 inverse
+template <class F> __global__ void fp2_op_kernel(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int reps) {
+    constexpr int L = F::L;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[L], y[L], r[L];
+    load_limbs<L>(x, a + i * L);
+    if (b) load_limbs<L>(y, b + i * L);
+    else limbs_copy<L>(y, x);
+    for (int k = 0; k < reps; k++) {
+        switch (op) {
+            case 0: F::mul(r, x, y); break;
+            case 1: F::add(r, x, y); break;
+            case 2: F::sub(r, x, y); break;
+            case 3: F::sqr(r, x); break;
+            case 4: F::dbl(r, x); break;
+            case 5: F::neg(r, x); break;
+            default: F::inv(r, x); break;
+        }
+        limbs_copy<L>(x, r);
+    }
+    store_limbs<L>(out + i * L, r);
+}
+
 template <class P> __global__ void ec_op_kernel(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
     using E = Ec<Fp<P>>;
     constexpr int L = P::L;
@@ -89,6 +113,10 @@ int fp_op_dispatch(int field, int op, const void *a, const void *b, void *out, s
         case 1: fp_op_kernel<BlsFr><<<blocks, 128, 0, st>>>(op, A, B, O, n, reps); break;
         case 2: fp_op_kernel<BnFq><<<blocks, 128, 0, st>>>(op, A, B, O, n, reps); break;
         case 3: fp_op_kernel<BnFr><<<blocks, 128, 0, st>>>(op, A, B, O, n, reps); break;
+        case 4:
+            if (op == 6 || op == 7) { set_last_error("into/from_bigint are not defined for Fq2"); return B200_EINVAL; }
+            fp2_op_kernel<Fp2<BlsFq>><<<blocks, 128, 0, st>>>(op, A, B, O, n, reps);
+            break;
         default: set_last_error("unknown field id"); return B200_EINVAL;
     }
     AB_LAUNCHED();

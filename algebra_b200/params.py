@@ -75,12 +75,14 @@ class G1Curve:
     ntt_field_id: int        # B200_FIELD_* of the scalar field
     fq: PrimeField
     fr: PrimeField
-    coeff_b: int
-    generator: tuple         # affine (x, y), canonical ints
+    coeff_b: object          # int (G1) or (c0, c1) (G2)
+    generator: tuple         # affine (x, y), canonical ints (G2: each coordinate is (c0, c1))
+    ext_degree: int = 1      # coordinates live in Fq (1) or Fq2 (2)
 
     @property
     def N(self) -> int:
-        return self.fq.limbs
+        """u64 limbs per coordinate"""
+        return self.fq.limbs * self.ext_degree
 
 
 BLS12_381_G1 = G1Curve(
@@ -88,5 +90,11 @@ BLS12_381_G1 = G1Curve(
     (3685416753713387016781088315183077757961620795782546409894578378688607592378376318836054947676345821548104185464507,
      1339506544944476473020471379941921221584933875938349620426543736416511423956333506472724655353366534992391756441569))
 BN254_G1 = G1Curve("bn254_g1", 1, 1, BN254_FQ, BN254_FR, 3, (1, 2))
-CURVES = {0: BLS12_381_G1, 1: BN254_G1}
+BLS12_381_G2 = G1Curve(
+    "bls12_381_g2", 2, 0, BLS12_381_FQ, BLS12_381_FR, (4, 4),
+    ((352701069587466618187139116011060144890029952792775240219908644239793785735715026873347600343865175952761926303160,
+      3059144344244213709971259814753781636986470325476647558659373206291635324768958432433509563104347017837885763365758),
+     (1985150602287291935568054521177171638300868978215655730859378665066344726373823718423869104263333984641494340347905,
+      927553665492332455747201965776037880757740193453592970025027978793976877002675564980949289727957565575433344219582)), 2)
+CURVES = {0: BLS12_381_G1, 1: BN254_G1, 2: BLS12_381_G2}
 SCALAR_FIELDS = {0: BLS12_381_FR, 1: BN254_FR}   # keyed by B200_FIELD_*

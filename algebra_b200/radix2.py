@@ -123,14 +123,28 @@ class Radix2EvaluationDomain:
         del keep
         return x
 
+    def _run_padded(self, x, inverse: bool):
+        """host input shorter (or longer) than the domain: only the given rows cross PCIe, the resize happens on the device"""
+        keep, offp = self._offset_ptr()
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty((self.size, 4), dtype=np.uint64)
+        _lib.check(_lib.lib().b200_ntt_fr_padded(self.field_id, x.ctypes.data_as(ctypes.c_void_p), x.shape[0], out.ctypes.data_as(ctypes.c_void_p),
+                                                 self.log_size_of_group, int(inverse), offp))
+        del keep
+        return out
+
     def fft(self, coeffs):
         """EvaluationDomain::fft (poly/src/domain/mod.rs:94-98): returns a new vector of `size` evaluations."""
+        if not _is_torch(coeffs):
+            return self._run_padded(coeffs, False)
         x = self._resize(coeffs)
         if self._shares(x, coeffs):
             x = x.clone() if _is_torch(x) else x.copy()
         return self._run(x, False)
 
     def ifft(self, evals):
+        if not _is_torch(evals):
+            return self._run_padded(evals, True)
         x = self._resize(evals)
         if self._shares(x, evals):
             x = x.clone() if _is_torch(x) else x.copy()

@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 # 32 x 148 SMs x 1.965 GHz = 9.31 T/s; the element-wise Fq multiplication kernel reaches 9.05 T/s of it
 # (profiles/r01_field_bench.jsonl), the synthetic carry-chain microbenchmark 8.5 T/s.
 IMAD_PEAK_WIDE_PER_S = 9.31e12
+IMAD_PEAK_SOURCE = "32 IMAD.WIDE/clk/SM x 148 SMs x 1.965 GHz (tools/imad_peak.cu: SASS-verified count, profiles/r02_imad_peak.jsonl)"
 
 
 def measured_peaks():
@@ -112,23 +113,38 @@ def run_reference(args):
     threads = C.num_threads()
     log_n = args.log_n_msm
     n = 1 << log_n
-    shrink = 8 if log_n > 20 else 1
+    # bounded sample: n/4 pairs per step (x4) above 2^22 unless --ref-full; the window is the one ark-ec would pick for the FULL
+    # problem (c = ln_without_floats(chunk)+2 for chunks of n / (threads/2) pairs, variable_base/mod.rs:445-449,521-535), so the
+    # sample does the same work per pair as the full run
+    shrink = 1 if (args.ref_full or log_n <= 22) else 4
     ns = n // shrink
+    c_full = C.window_size(max(1, n // max(1, threads // 2)))
     cv = O.BLS12_381
-    # synthetic inputs on the host: P_i = P_0 + i*Q chain would need CPU EC work; reuse a small block of real points
-    # (arithmetic cost is data-independent) tiled to ns, scalars uniform in [0, r)
     rng = np.random.default_rng(args.seed)
-    blk = 1 << 10
-    ks = [int(x) for x in rng.integers(1, 1 << 62, size=64)]
-    pts = cv.encode_affine([cv.mul(cv.G, k) for k in ks])
-    bases = np.ascontiguousarray(np.tile(pts, (ns // 64 + 1, 1))[:ns])
+    bases, base_kind = None, ""
+    try:   # real distinct bases b_i*G: produced by the device generator when a GPU is present (input preparation, not the timed path)
+        import torch
+        if torch.cuda.is_available():
+            from algebra_b200 import _lib
+            d = torch.empty((ns, 12), dtype=torch.int64, device="cuda")
+            _lib.check(_lib.lib().b200_gen_bases_dev(0, args.seed, ns, d.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+            bases = d.cpu().numpy().view(np.uint64)
+            del d
+            torch.cuda.empty_cache()
+            base_kind = "distinct bases b_i*G"
+    except Exception:
+        bases = None
+    if bases is None:   # no GPU: a block of 64 real points tiled (the arithmetic cost is data-independent)
+        ks = [int(x) for x in rng.integers(1, 1 << 62, size=64)]
+        pts = cv.encode_affine([cv.mul(cv.G, k) for k in ks])
+        bases = np.ascontiguousarray(np.tile(pts, (ns // 64 + 1, 1))[:ns])
+        base_kind = "64 distinct points tiled"
     scal = rng.integers(0, 1 << 64, size=(ns, 4), dtype=np.uint64)
     scal[:, 3] &= np.uint64((1 << 62) - 1)
-    del blk
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        C.msm(0, bases, scal, threads=threads)
+        C.msm(0, bases, scal, threads=threads, c=c_full)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -142,8 +158,8 @@ def run_reference(args):
         t0 = time.perf_counter()
         C.lib().ark_fft(1, x.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), args.log_n_ntt, 0, None, threads)
         tn.append(time.perf_counter() - t0)
-    sample = f"MSM: {ns} of {n} pairs (1/{shrink}) on {threads} threads, time x{shrink}; window rule and chunking of ark-ec " \
-             f"(c={C.window_size(max(1, ns // max(1, threads // 2)))} per chunk); NTT: full 2^{args.log_n_ntt}"
+    sample = f"MSM: {ns} of {n} pairs (1/{shrink}) on {threads} threads, time x{shrink}, {base_kind}; chunking of ark-ec with the " \
+             f"window of the full problem (c={c_full} per chunk of n/{max(1, threads // 2)}); NTT: full 2^{args.log_n_ntt}"
     v = 1.0 / t_full
     line = {
         "impl": "reference", "metric": "BLS12-381 G1 MSM/s @2^%d" % log_n, "value": v, "unit": "MSM/s", "n_gpus": args.gpus,
@@ -176,6 +192,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-ntt", action="store_true", help="skip the NTT leg (MSM tuning runs)")
+    ap.add_argument("--ref-full", action="store_true", help="--impl reference: time the full n instead of the n/4 sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -294,29 +311,36 @@ def main():
             verified = bool((got == want).all())
             del C
 
-    # ---------------- e2e: host buffers through the C ABI (pinned host memory, H2D + D2H inside the timed region)
+    # ---------------- e2e: host buffers through the C ABI, H2D + D2H inside the timed region; measured from pinned host
+    # memory (the headline e2e, as the contract asks) and from ordinary pageable memory (what a Rust Vec is): the library
+    # stages pageable sources through its pinned ring
     e2e = None
     if not args.no_e2e:
+        def timed_host(hb, hs, steps):
+            msm_step(hb, hs)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                r = msm_step(hb, hs)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            return max_over_ranks(dt) / steps, r
+        e2e_steps = max(1, min(args.steps, 3))
         h_bases = torch.empty((n_local, 2 * N), dtype=torch.int64).pin_memory()
         h_scal = torch.empty((n_local, 4), dtype=torch.int64).pin_memory()
         h_bases.copy_(d_bases)
         h_scal.copy_(d_scal)
-        hb, hs = h_bases.numpy().view(np.uint64), h_scal.numpy().view(np.uint64)
-        e2e_steps = max(1, min(args.steps, 3))
-        msm_step(hb, hs)
-        t0 = 0.0
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            r2 = msm_step(hb, hs)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        barrier()
-        dt = max_over_ranks(dt) / e2e_steps
-        e2e = {"value": 1.0 / dt, "unit": "MSM/s", "ms_per_step": dt * 1e3, "steps": e2e_steps,
+        dt, r2 = timed_host(h_bases.numpy().view(np.uint64), h_scal.numpy().view(np.uint64), e2e_steps)
+        e2e = {"value": 1.0 / dt, "unit": "MSM/s", "ms_per_step": dt * 1e3, "steps": e2e_steps, "host_memory": "pinned",
                "h2d_bytes_per_step": int(n_local * (2 * N * 8 + 32)) * world, "d2h_bytes_per_step": 3 * N * 8 * world,
                "same_result": bool((ab.into_affine(cv, r2) == ab.into_affine(cv, res)).all())}
-        del h_bases, h_scal, hb, hs
+        pb, ps = h_bases.numpy().copy(), h_scal.numpy().copy()       # pageable copies
+        del h_bases, h_scal
+        dtp, r3 = timed_host(pb.view(np.uint64), ps.view(np.uint64), e2e_steps)
+        e2e["pageable"] = {"value": 1.0 / dtp, "unit": "MSM/s", "ms_per_step": dtp * 1e3,
+                           "same_result": bool((ab.into_affine(cv, r3) == ab.into_affine(cv, res)).all())}
+        del pb, ps
 
     # ---------------- NTT leg (replicas only for N > 1)
     del d_bases, d_b, d_scal
@@ -374,6 +398,14 @@ def main():
         modmuls, wide, byts = msm_work(n_local, c, W, 2 * N)
         acc_s = phase["accumulate"] * 1e-3
         acc_wide = 10.0 * n_local * W * (2 * (2 * N) ** 2 + 2 * N)
+        # multiplications actually executed: 4 affine levels leave 1/16 of the entries to the XYZZ kernel (10 each), the levels cost
+        # 6 + 570/batch (~6.6) per addition; bucket reduction ~28 per bucket; BN254 runs without levels
+        lv = 4 if N == 6 else 0
+        executed_modmuls = n_local * W * ((1 - 0.5 ** lv) * 6.6 + 0.5 ** lv * 10.0) + 28.0 * (1 << (c - 1)) * W
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tp) and world == 1 and args.log_n_msm == 26 and args.curve == 0:
+            traffic = json.load(open(tp))
         line = {
             "metric": "BLS12-381 G1 MSM/s @2^%d" % args.log_n_msm if args.curve == 0 else "BN254 G1 MSM/s @2^%d" % args.log_n_msm,
             "value": 1000.0 / ms_msm, "unit": "MSM/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -385,17 +417,22 @@ def main():
                        "l2": "inputs (>= 2 GiB) larger than L2; no flush needed", "seed": args.seed, "verified_vs_sum_identity": verified},
             "clocks": clocks,
             "phases_ms": phase,
-            "roofline": {"bound": "hbm", "kernel": "accumulation phase: msm_pair_add_kernel (batched-affine levels) + msm_accumulate_kernel", "achieved": byts / acc_s / 1e9 if acc_s else None,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": (byts / acc_s / 1e9) / hbm_peak if acc_s else None,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "compute-bound kernel: see imad_roofline (SURVEY.md §8d: MSM is bound by the integer-multiply pipe)"},
-            "imad_roofline": {"bound": "int32 wide-MAD pipe", "kernel": "accumulation phase: msm_pair_add_kernel + msm_accumulate_kernel",
-                              "achieved": acc_wide / acc_s / 1e12 if acc_s else None, "peak": IMAD_PEAK_WIDE_PER_S / 1e12,
-                              "unit": "T wide-MAD/s", "frac": (acc_wide / acc_s) / IMAD_PEAK_WIDE_PER_S if acc_s else None,
-                              "peak_source": "32 IMAD.WIDE/clk/SM measured (profiles/r01_imad_microbench.jsonl) x 148 SMs x 1.965 GHz",
-                              "algorithmic": "10 Fq modmuls x (2L^2+L = 300) wide MADs per bucket addition, n*W additions (the reference's "
-                                             "XYZZ formula); the batched-affine levels execute ~6.6 modmuls for 15/16 of the additions, "
-                                             "so this fraction can exceed 1"},
+            # MSM is bound by the integer-multiply pipe, so the roofline block is the IMAD one: algorithmic wide MADs of
+            # the WHOLE step (10*n*W + 14*2^c*W Fq multiplications x 300) over the step time, against the measured IMAD.WIDE issue rate
+            "roofline": {"bound": "imad", "kernel": "whole MSM step (dominant kernel: msm_pair_add*_kernel, batched-affine levels)",
+                         "achieved": wide / (ms_msm * 1e-3) / 1e12, "peak": IMAD_PEAK_WIDE_PER_S / 1e12, "unit": "T wide-MAD/s",
+                         "frac": wide / (ms_msm * 1e-3) / IMAD_PEAK_WIDE_PER_S,
+                         "frac_accumulation_phase": (acc_wide / acc_s) / IMAD_PEAK_WIDE_PER_S if acc_s else None,
+                         "frac_executed": (executed_modmuls * 300.0 if N == 6 else executed_modmuls * 136.0) / (ms_msm * 1e-3) / IMAD_PEAK_WIDE_PER_S,
+                         "traffic": traffic.get("msm_dominant_kernel_dram_bytes_per_launch"),
+                         "traffic_whole_step": traffic.get("msm_step_dram_bytes"),
+                         "algorithmic_bytes": byts,
+                         "peak_source": IMAD_PEAK_SOURCE,
+                         "note": "frac = the reference's 10-multiplication XYZZ formula per bucket addition; frac_executed = multiplications "
+                                 "actually issued (batched-affine additions cost ~6.6 each); traffic = dram read+write bytes from the ncu "
+                                 "capture of this command committed as profiles/r02_traffic.json"},
+            "hbm_roofline": {"bound": "hbm", "achieved": byts / (ms_msm * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": byts / (ms_msm * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
             "gpu_launches": launches,
             "e2e": e2e,
             "cpu_baseline": cpu,
@@ -403,7 +440,9 @@ def main():
                     "ms_per_step": ms_ntt, "ifft_ms_per_step": ms_intt, "scaling": "replicas only", "gpu_launches": ntt_launches,
                     "roundtrip_ok": ntt_ok, "e2e": ntt_e2e,
                     "roofline": {"bound": "hbm", "achieved": 64.0 * n_ntt / (ms_ntt * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": 64.0 * n_ntt / (ms_ntt * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src},
+                                 "frac": 64.0 * n_ntt / (ms_ntt * 1e-3) / 1e9 / hbm_peak,
+                                 "traffic": traffic.get("ntt_dram_bytes_per_transform") if args.log_n_ntt == 24 else None, "peak_source": peak_src,
+                                 "note": "contractual HBM figure; the transform is bound by the integer pipe (imad_roofline)"},
                     "imad_roofline": {"achieved": 136.0 * (n_ntt / 2 * args.log_n_ntt) / (ms_ntt * 1e-3) / 1e12,
                                       "peak": IMAD_PEAK_WIDE_PER_S / 1e12, "unit": "T wide-MAD/s",
                                       "frac": 136.0 * (n_ntt / 2 * args.log_n_ntt) / (ms_ntt * 1e-3) / IMAD_PEAK_WIDE_PER_S}},

@@ -135,6 +135,11 @@ int b200_g1_into_affine(int curve, const uint64_t *xyz, uint64_t *out_xy);
  * Returns B200_ETOOLARGE when log_n > TWO_ADICITY (where Radix2EvaluationDomain::new gives None).
  * --------------------------------------------------------------------------------------------- */
 int b200_ntt_fr(int field, uint64_t *data, uint32_t log_n, int inverse, const uint64_t *coset_offset);
+/* Same with the resize of `fft_in_place` (radix2/mod.rs:140-147) folded in: `in` holds len_in <= 2^log_n elements (longer inputs
+ * are truncated), only those cross PCIe, the zero padding is produced on the device; `out` receives all 2^log_n results (may be
+ * `in` if it has the room).  This is the transfer-side half of the reference's degree-aware route (fft.rs:29-71); its arithmetic
+ * half saves no multiplications on this kernel (a butterfly with a zero upper input still needs its twiddle product). */
+int b200_ntt_fr_padded(int field, const uint64_t *in, size_t len_in, uint64_t *out, uint32_t log_n, int inverse, const uint64_t *coset_offset);
 /* device-resident variant: d_data is a device pointer; coset_offset stays a host pointer. */
 int b200_ntt_fr_dev(int field, void *d_data, uint32_t log_n, int inverse, const uint64_t *coset_offset,
                     void *stream);
@@ -172,7 +177,7 @@ int b200_g1_normalize_batch_dev(int curve, const void *d_xyz, size_t n, void *d_
 /* ---------------------------------------------------------------------------------------------
  * Element-wise primitive kernels (parity tests and the field micro-benchmark, cf.
  * bench-templates/src/macros/field.rs:69-155).  Device pointers; 1 thread per element.
- *   b200_fp_op_dev  field: 0 BLS Fq, 1 BLS Fr, 2 BN254 Fq, 3 BN254 Fr
+ *   b200_fp_op_dev  field: 0 BLS Fq, 1 BLS Fr, 2 BN254 Fq, 3 BN254 Fr, 4 BLS Fq2 (12 u64 per element: c0 | c1; ops 6/7 undefined)
  *                   op: 0 mul 1 add 2 sub 3 square 4 double 5 neg 6 into_bigint 7 from_bigint 8 inverse
  *   b200_ec_op_dev  op: 0 bucket+=affine 1 bucket-=affine 2 bucket+=bucket 3 bucket.double
  *                       4 bucket->jacobian 5 jacobian->affine 6 jacobian+=jacobian 7 jacobian.double

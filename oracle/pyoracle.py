@@ -612,3 +612,167 @@ def rand_field(field: Field, n: int, seed: int) -> list[int]:
         if v < field.p:
             out.append(v)
     return out
+
+
+# --------------------------------------------------------------------------
+# G2 of BLS12-381 (curves/bls12_381/src/curves/g2.rs:54-90,218-236): y^2 = x^3 + 4(u + 1) over Fq2 = Fq[u]/(u^2 + 1)
+# (curves/bls12_381/src/fields/fq2.rs:10-24).  Elements are pairs (c0, c1) of canonical ints; the limb encoding is
+# QuadExtField's in-memory order c0 | c1 (ff/src/fields/models/quadratic_extension.rs:105-113), each 6 Montgomery u64.
+# Checker-only code: math-level restatement (Jacobian over Fq2), pinned on the reference's own i*G2 table
+# (tests/test_oracle_golden.py).
+# --------------------------------------------------------------------------
+class Fq2:
+    def __init__(self, fq: Field):
+        self.fq, self.p = fq, fq.p
+
+    def add(self, a, b):
+        return ((a[0] + b[0]) % self.p, (a[1] + b[1]) % self.p)
+
+    def sub(self, a, b):
+        return ((a[0] - b[0]) % self.p, (a[1] - b[1]) % self.p)
+
+    def neg(self, a):
+        return ((-a[0]) % self.p, (-a[1]) % self.p)
+
+    def mul(self, a, b):
+        p = self.p
+        return ((a[0] * b[0] - a[1] * b[1]) % p, (a[0] * b[1] + a[1] * b[0]) % p)
+
+    def sqr(self, a):
+        return self.mul(a, a)
+
+    def smul(self, a, k: int):
+        return (a[0] * k % self.p, a[1] * k % self.p)
+
+    def inv(self, a):
+        p = self.p
+        n = pow((a[0] * a[0] + a[1] * a[1]) % p, -1, p)
+        return (a[0] * n % p, (-a[1]) * n % p)
+
+    def is_zero(self, a):
+        return a[0] % self.p == 0 and a[1] % self.p == 0
+
+
+class CurveG2:
+    def __init__(self, cid: int, name: str, fq: Field, fr: Field, b, gx, gy):
+        self.id, self.name, self.fq, self.fr, self.b = cid, name, fq, fr, b
+        self.F = Fq2(fq)
+        self.G = (gx, gy)
+        self.scalar_bits = fr.bits
+        assert self.on_curve(self.G)
+
+    def on_curve(self, P) -> bool:
+        if P is None:
+            return True
+        F = self.F
+        x, y = P
+        return F.is_zero(F.sub(F.sqr(y), F.add(F.mul(F.sqr(x), x), self.b)))
+
+    def neg(self, P):
+        return None if P is None else (P[0], self.F.neg(P[1]))
+
+    def _jac_dbl(self, P):
+        if P is None:
+            return None
+        F = self.F
+        X, Y, Z = P
+        if F.is_zero(Y):
+            return None
+        A, B = F.sqr(X), F.sqr(Y)
+        C = F.sqr(B)
+        D = F.smul(F.mul(X, B), 4)
+        E = F.smul(A, 3)
+        X3 = F.sub(F.sqr(E), F.smul(D, 2))
+        Y3 = F.sub(F.mul(E, F.sub(D, X3)), F.smul(C, 8))
+        return (X3, Y3, F.smul(F.mul(Y, Z), 2))
+
+    def _jac_add(self, P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        F = self.F
+        X1, Y1, Z1 = P
+        X2, Y2, Z2 = Q
+        Z1Z1, Z2Z2 = F.sqr(Z1), F.sqr(Z2)
+        U1, U2 = F.mul(X1, Z2Z2), F.mul(X2, Z1Z1)
+        S1, S2 = F.mul(F.mul(Y1, Z2), Z2Z2), F.mul(F.mul(Y2, Z1), Z1Z1)
+        if U1 == U2:
+            return self._jac_dbl(P) if S1 == S2 else None
+        H, Rr = F.sub(U2, U1), F.sub(S2, S1)
+        HH = F.sqr(H)
+        HHH = F.mul(H, HH)
+        V = F.mul(U1, HH)
+        X3 = F.sub(F.sub(F.sqr(Rr), HHH), F.smul(V, 2))
+        Y3 = F.sub(F.mul(Rr, F.sub(V, X3)), F.mul(S1, HHH))
+        return (X3, Y3, F.mul(F.mul(Z1, Z2), H))
+
+    def jac_to_affine(self, J):
+        if J is None or self.F.is_zero(J[2]):
+            return None
+        F = self.F
+        zi = F.inv(J[2])
+        zi2 = F.sqr(zi)
+        return (F.mul(J[0], zi2), F.mul(F.mul(J[1], zi2), zi))
+
+    def add(self, P, Q):
+        lift = lambda A: None if A is None else (A[0], A[1], (1, 0))
+        return self.jac_to_affine(self._jac_add(lift(P), lift(Q)))
+
+    def mul(self, P, k: int):
+        k %= self.fr.p
+        if P is None or k == 0:
+            return None
+        acc, base = None, (P[0], P[1], (1, 0))
+        for bit in bin(k)[2:]:
+            acc = self._jac_dbl(acc)
+            if bit == "1":
+                acc = self._jac_add(acc, base)
+        return self.jac_to_affine(acc)
+
+    # -- limb encodings: affine = x.c0 | x.c1 | y.c0 | y.c1 (24 u64), infinity = all zero --------------------------------
+    def encode_affine(self, pts) -> np.ndarray:
+        N = self.fq.N
+        out = np.zeros((len(pts), 4 * N), dtype=np.uint64)
+        for i, P in enumerate(pts):
+            if P is None:
+                continue
+            for k, v in enumerate((P[0][0], P[0][1], P[1][0], P[1][1])):
+                out[i, k * N:(k + 1) * N] = self.fq.limbs(self.fq.to_mont(v))
+        return out
+
+    def decode_affine(self, arr):
+        N = self.fq.N
+        arr = np.asarray(arr, dtype=np.uint64).reshape(-1, 4 * N)
+        pts = []
+        for row in arr:
+            v = [self.fq.from_limbs(row[k * N:(k + 1) * N]) for k in range(4)]
+            if not any(v):
+                pts.append(None)
+            else:
+                c = [self.fq.from_mont(t) for t in v]
+                pts.append(((c[0], c[1]), (c[2], c[3])))
+        return pts
+
+    def decode_jacobian(self, arr):
+        N = self.fq.N
+        arr = np.asarray(arr, dtype=np.uint64).reshape(6 * N)
+        v = [self.fq.from_mont(self.fq.from_limbs(arr[k * N:(k + 1) * N])) for k in range(6)]
+        return self.jac_to_affine(((v[0], v[1]), (v[2], v[3]), (v[4], v[5])))
+
+    def naive_msm(self, bases, scalars):
+        acc = None
+        for P, s in zip(bases, scalars):
+            Q = self.mul(P, s)
+            if Q is not None:
+                acc = self._jac_add(acc, (Q[0], Q[1], (1, 0)))
+        return self.jac_to_affine(acc)
+
+
+BLS12_381_G2 = CurveG2(
+    2, "bls12_381_g2", BLS12_381_FQ, BLS12_381_FR, (4, 4),
+    (352701069587466618187139116011060144890029952792775240219908644239793785735715026873347600343865175952761926303160,
+     3059144344244213709971259814753781636986470325476647558659373206291635324768958432433509563104347017837885763365758),
+    (1985150602287291935568054521177171638300868978215655730859378665066344726373823718423869104263333984641494340347905,
+     927553665492332455747201965776037880757740193453592970025027978793976877002675564980949289727957565575433344219582))
+CURVES[2] = BLS12_381_G2

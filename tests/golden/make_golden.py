@@ -17,6 +17,8 @@ Sources (all under /root/reference; parsed as DATA, never imported or copied as 
 
 Outputs (committed):
   tests/golden/bls12_381_g1_multiples.npy   uint64 (1000, 12): canonical LE limbs x|y, (0,0)=inf
+  tests/golden/bls12_381_g2_multiples.npy   uint64 (1000, 24): x.c0|x.c1|y.c0|y.c1 of i*G2 from
+      curves/bls12_381/src/curves/tests/g2_uncompressed_valid_test_vectors.dat
   tests/golden/kats.json                    constants + Fq2 KATs as hex strings
 """
 import json
@@ -59,6 +61,26 @@ def g1_table():
         for j in range(6):
             tab[i, j] = (x >> (64 * j)) & (2**64 - 1)
             tab[i, 6 + j] = (y >> (64 * j)) & (2**64 - 1)
+    return tab
+
+
+def g2_table():
+    """[0*G2 .. 999*G2], zkcrypto order x.c1 | x.c0 | y.c1 | y.c0 big-endian (curves/bls12_381/src/curves/util.rs:211-256) ->
+    uint64 (1000, 24): canonical LE limbs of x.c0 | x.c1 | y.c0 | y.c1 (arkworks' QuadExtField order), all-zero = infinity"""
+    raw = open(f"{REF}/curves/bls12_381/src/curves/tests/g2_uncompressed_valid_test_vectors.dat", "rb").read()
+    assert len(raw) == 192000
+    tab = np.zeros((1000, 24), dtype=np.uint64)
+    for i in range(1000):
+        rec = bytearray(raw[192 * i:192 * (i + 1)])
+        flags = rec[0] >> 5
+        rec[0] &= 0x1F
+        assert not (flags & 4)
+        xc1, xc0, yc1, yc0 = (int.from_bytes(rec[48 * k:48 * (k + 1)], "big") for k in range(4))
+        if flags & 2:
+            assert xc1 == xc0 == yc1 == yc0 == 0 and i == 0
+        for k, v in enumerate((xc0, xc1, yc0, yc1)):
+            for j in range(6):
+                tab[i, 6 * k + j] = (v >> (64 * j)) & (2**64 - 1)
     return tab
 
 
@@ -106,6 +128,7 @@ def fq_field_kats():
 
 def main():
     np.save(os.path.join(HERE, "bls12_381_g1_multiples.npy"), g1_table())
+    np.save(os.path.join(HERE, "bls12_381_g2_multiples.npy"), g2_table())
     kats = {
         "source": "arkworks-rs/algebra v0.6.0 (af564e48) — see make_golden.py docstring for file:line",
         "bls12_381_fq": fq_constants(),

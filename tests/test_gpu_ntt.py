@@ -170,8 +170,8 @@ def test_poly_mul_and_interpolate():
         A, B = fr.encode(a), fr.encode(b)
         got = ab.poly_mul(0, A, B)
         assert fr.decode(got) == want
-        gd = from_dev(ab.poly_mul(0, to_dev(A), to_dev(B)))
-        assert fr.decode(gd[: la + lb - 1]) == want and not gd[la + lb - 1:].any()
+        gd = from_dev(ab.poly_mul(0, to_dev(A), to_dev(B)))          # device path trims like the host path
+        assert gd.shape[0] == la + lb - 1 and fr.decode(gd) == want
     assert ab.poly_mul(0, np.zeros((0, 4), np.uint64), fr.encode([1, 2])).shape == (0, 4)
     dom = ab.Radix2EvaluationDomain.new(0, 64)
     coeffs = fr.encode([rnd.randrange(fr.p) for _ in range(40)])

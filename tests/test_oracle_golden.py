@@ -249,3 +249,35 @@ def test_root_of_unity_constants():
     assert hex(d.group_gen) == "0x291cf6d68823e6876e0bcd91ee76273072cf6a8029b7d7bc92cf4deb77bd779c"
     assert pow(d.group_gen, 1 << 23, fr.p) == fr.p - 1
     assert O.BN254_FR.two_adicity == 28
+
+
+def test_g2_oracle_pinned_on_reference_table(golden_dir, kats):
+    """The G2 oracle (Fq2 arithmetic + Jacobian group law, oracle/pyoracle.py) against the reference's own
+    [0*G2 .. 999*G2] table (curves/bls12_381/src/curves/tests/g2_uncompressed_valid_test_vectors.dat) and Fq2 KATs."""
+    g2 = O.BLS12_381_G2
+    tab = np.load(os.path.join(golden_dir, "bls12_381_g2_multiples.npy"))
+
+    def row(i):
+        v = [sum(int(tab[i, 6 * k + j]) << (64 * j) for j in range(6)) for k in range(4)]
+        return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+
+    assert row(0) is None and row(1) == g2.G
+    acc = None
+    for i in range(1000):                                  # i*G2 by repeated addition == table
+        assert row(i) == acc, i
+        acc = g2.add(acc, g2.G)
+    rnd = random.Random(9)
+    for i in [2, 3, 999] + [rnd.randrange(1000) for _ in range(10)]:
+        assert g2.mul(g2.G, i) == row(i)                   # double-and-add
+    assert g2.mul(g2.G, g2.fr.p - 5) == g2.neg(row(5)) and g2.mul(g2.G, g2.fr.p) is None
+    assert g2.naive_msm([row(3), row(10), None, row(7)], [5, 2, 9, g2.fr.p - 1]) == row(28)
+    enc = g2.encode_affine([row(5), None])
+    assert g2.decode_affine(enc) == [row(5), None] and not enc[1].any()
+    f = kats["bls12_381_fq_field"]
+    F = g2.F
+    a = tuple(int(x, 16) for x in f["fq2_mul"]["a"]); b = tuple(int(x, 16) for x in f["fq2_mul"]["b"])
+    assert F.mul(a, b) == tuple(int(x, 16) for x in f["fq2_mul"]["r"])
+    a = tuple(int(x, 16) for x in f["fq2_square"]["a"])
+    assert F.sqr(a) == tuple(int(x, 16) for x in f["fq2_square"]["r"])
+    a = tuple(int(x, 16) for x in f["fq2_inverse"]["a"])
+    assert F.inv(a) == tuple(int(x, 16) for x in f["fq2_inverse"]["r"])

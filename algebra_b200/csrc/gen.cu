@@ -69,8 +69,10 @@ template <class G> __global__ void gen_table_kernel(uint32_t *table) {
     typename E::J base, acc;
     G::generator(base.x, base.y);
     F::set_one(base.z);
+#pragma unroll 1
     for (int k = 0; k < 8 * w; k++) E::jac_dbl(base);
     E::jac_set_zero(acc);
+#pragma unroll 1
     for (int bit = 7; bit >= 0; bit--) {
         E::jac_dbl(acc);
         if ((d >> bit) & 1) E::jac_add(acc, base);
@@ -91,11 +93,13 @@ template <class G> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64
     typename E::B pts[kGenBatch];
     uint32_t prefix[kGenBatch][L];
     int cnt = 0;
+#pragma unroll 1
     for (; cnt < kGenBatch && i0 + cnt < n; cnt++) {
         uint64_t b = splitmix64_at(seed, i0 + cnt) | 1ull;
         if (bvals) bvals[i0 + cnt] = b;
         typename E::B acc;
         E::xyzz_set_zero(acc);
+#pragma unroll 1
         for (int w = 0; w < 8; w++) {
             uint32_t d = (uint32_t)(b >> (8 * w)) & 255u;
             uint32_t px[L], py[L];
@@ -111,6 +115,7 @@ template <class G> __global__ void __launch_bounds__(64) gen_bases_kernel(uint64
     // b*G with b odd and < 2^64 << r is never the identity, so every zzz is invertible
     uint32_t inv[L];
     F::inv(inv, prefix[cnt - 1]);
+#pragma unroll 1
     for (int k = cnt - 1; k >= 0; k--) {
         uint32_t zi[L], t[L], ax[L], ay[L];
         if (k > 0) F::mul(zi, inv, prefix[k - 1]);
@@ -140,8 +145,10 @@ template <class P> __global__ void batch_table_kernel(LimbArg<P::L> bx, LimbArg<
 #pragma unroll
         for (int i = 0; i < L; i++) { base.x[i] = bx.v[i]; base.y[i] = by.v[i]; base.z[i] = P::ONE(i); }
     }
+#pragma unroll 1
     for (int k = 0; k < 8 * w; k++) E::jac_dbl(base);
     E::jac_set_zero(acc);
+#pragma unroll 1
     for (int bit = 7; bit >= 0; bit--) {
         E::jac_dbl(acc);
         if ((d >> bit) & 1) E::jac_add(acc, base);
@@ -159,12 +166,14 @@ template <class P, int B> __device__ __forceinline__ void xyzz_batch_to_affine(X
     constexpr int L = P::L;
     uint32_t prefix[B][L], run[L];
     F::set_one(run);
+#pragma unroll 1
     for (int k = 0; k < cnt; k++) {
         limbs_copy<L>(prefix[k], run);                        // product of the non-identity zzz before k
         if (!E::xyzz_is_zero(pts[k])) F::mul(run, run, pts[k].zzz);
     }
     uint32_t inv[L];
     F::inv(inv, run);
+#pragma unroll 1
     for (int k = cnt - 1; k >= 0; k--) {
         uint32_t ax[L], ay[L];
         if (E::xyzz_is_zero(pts[k])) {
@@ -195,12 +204,14 @@ template <class PQ, class PR> __global__ void __launch_bounds__(64) batch_mul_ke
     if (i0 >= n) return;
     typename E::B pts[kGenBatch];
     int cnt = 0;
+#pragma unroll 1
     for (; cnt < kGenBatch && i0 + cnt < n; cnt++) {
         uint32_t s[8], k[8];
         load_limbs_nc<8>(s, scalars + (i0 + cnt) * 8);
         FR::from_mont(k, s);
         typename E::B acc;
         E::xyzz_set_zero(acc);
+#pragma unroll 1
         for (int w = 0; w < windows; w++) {
             uint32_t d = (k[w >> 2] >> (8 * (w & 3))) & 255u;
             if (d == 0) continue;
@@ -223,6 +234,7 @@ template <class P> __global__ void __launch_bounds__(64) normalize_batch_kernel(
     if (i0 >= n) return;
     Xyzz<P::L> pts[kGenBatch];
     int cnt = 0;
+#pragma unroll 1
     for (; cnt < kGenBatch && i0 + cnt < n; cnt++) {
         const uint32_t *p = jac + (i0 + cnt) * 3 * L;
         uint32_t z[L];

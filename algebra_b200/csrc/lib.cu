@@ -14,12 +14,12 @@ int ensure_device_init() {
     AB_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_init_mutex);
     if (dev < 64 && g_inited[dev]) return 0;
-    // Freed stream-ordered scratch stays cached up to a BOUNDED amount (default 48 GiB, B200_POOL_RETAIN_GB read once): enough for
+    // Freed stream-ordered scratch stays cached up to a BOUNDED amount (default 96 GiB, B200_POOL_RETAIN_GB read once): enough for
     // the scratch of a 2^26 MSM to be reused by the next call without re-allocation, while anything above it goes back to the
     // driver at the next synchronisation instead of starving other allocators of the process (e.g. PyTorch's).
     static const uint64_t retain = [] {
         const char *e = getenv("B200_POOL_RETAIN_GB");
-        const double gb = e ? atof(e) : 48.0;
+        const double gb = e ? atof(e) : 96.0;
         return (uint64_t)((gb < 0 ? 0 : gb) * (double)(1ull << 30));
     }();
     cudaMemPool_t pool;

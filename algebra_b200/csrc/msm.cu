@@ -165,14 +165,19 @@ __global__ void __launch_bounds__(256) msm_pairmap_kernel(const uint32_t *__rest
 // Options of a call.  Defaults come from the per-thread setters (b200_set_msm_window / _affine_levels) and, for the tuning
 // knobs without a public setter, from environment variables read ONCE per process (never on the call path).
 struct EnvKnobs {
-    int pair_variant = 2;                 // 1 = thread-contiguous batches, 2 = warp-interleaved + cp.async staging
-    double level_budget_bytes = 24e9;     // scratch allowed for the affine level arrays (window groups are sized to fit)
+    int pair_variant = 2;                 // levels >= 2: 1 = thread-contiguous batches, 2 = warp-interleaved + cp.async staging
+    int pair_variant_l1 = 1;              // level 1 (random gathers from the bases): measured 141.7 ms (1) vs 171.1 ms (2) @2^26
+    double level_budget_bytes = 72e9;     // scratch allowed for the affine level arrays (window groups are sized to fit); also capped
+                                          // by 60 % of the free device memory at the start of the call.  Measured @2^26 (accumulation
+                                          // phase): no groups (63 GB of levels) 280 ms, 2 groups (48 GB budget) 296 ms, 4 groups (24 GB) 306 ms,
+                                          // 10 groups (8 GB) 392 ms — groups shorten the batches of the later levels
     int shared_inv = 1;                   // one field inversion per block (Montgomery's trick across the block) instead of per thread
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
     EnvKnobs() {
         if (const char *e = getenv("B200_MSM_PAIR_VARIANT")) pair_variant = atoi(e) == 1 ? 1 : 2;
+        if (const char *e = getenv("B200_MSM_PAIR_VARIANT_L1")) pair_variant_l1 = atoi(e) == 2 ? 2 : 1;
         if (const char *e = getenv("B200_MSM_LEVEL_BUDGET_GB")) { double v = atof(e); if (v > 0.01) level_budget_bytes = v * 1e9; }
         if (const char *e = getenv("B200_MSM_SHARED_INV")) shared_inv = atoi(e) != 0;
         min_batch = shared_inv ? 96 : 256;   // overhead per addition: 590/(4*batch) multiplications shared, 570/batch per thread
@@ -281,6 +286,16 @@ struct EventSet {
     }
 };
 
+// bytes the default pool holds beyond what is in use: they count as available for this call's scratch
+static double pool_reserved_bytes() {
+    int dev = 0;
+    cudaMemPool_t pool;
+    uint64_t reserved = 0, used = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return 0.0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess) return 0.0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) return 0.0;
+    return reserved > used ? (double)(reserved - used) : 0.0;
+}
 static int sm_count() {
     static thread_local int cached_dev = -1, cached = 148;
     int dev = 0;
@@ -411,7 +426,6 @@ template <class C> struct MsmSession final : MsmSessionBase {
     int reduce_group(const uint32_t *bas, size_t b0, size_t b1, size_t group_entries, int levels, uint32_t *target) {
         const size_t nbg = b1 - b0;
         const bool forced = levels_opt >= 0;
-        const int variant = env_knobs().pair_variant;
         size_t cur_entries = group_entries;   // upper bound on the entries of the current level
         const uint32_t *cur_src = sorted, *cur_offsets = offsets + b0;
         uint32_t *lvl_pts[2] = {nullptr, nullptr}, *lvl_off[2] = {nullptr, nullptr};
@@ -435,6 +449,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
             msm_halve_counts_kernel<<<(unsigned)((nbg + 255) / 256), 256, 0, st>>>(cur_offsets, (uint32_t)nbg, counts);
             AB_LAUNCHED();
             if (int rc = scan(counts, nbg, off2)) return rc;
+            const int variant = lv == 0 ? env_knobs().pair_variant_l1 : env_knobs().pair_variant;
             uint32_t *pairmap = nullptr;
             if (variant == 2) {
                 if (int rc = arena.alloc(&pairmap, out_cap * 4)) return rc;
@@ -511,7 +526,10 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 // window groups: the level arrays of one group (level 1: entries/2 affine points, level 2: half of that, two
                 // levels alive at a time) must fit the scratch budget; groups are whole windows, balanced in size
                 const double per_window = ((double)nk * 0.5 + (double)g.nb * 0.5) * 2 * L * 4 * 1.5 + (double)nk * 0.5 * 4;
-                int gw = (int)std::floor(env_knobs().level_budget_bytes / per_window);
+                double budget = env_knobs().level_budget_bytes;
+                size_t free_b = 0, total_b = 0;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min(budget, 0.6 * (double)free_b + pool_reserved_bytes());
+                int gw = (int)std::floor(budget / per_window);
                 // ... and a group must give every resident thread a batch of >= min_batch additions at level 1
                 const int gw_min = (int)std::ceil((double)env_knobs().min_batch * (double)sm_count() * 512.0 / ((double)nk * 0.5));
                 gw = std::max(std::max(1, gw_min), std::min(g.W, gw));
@@ -544,10 +562,11 @@ template <class C> struct MsmSession final : MsmSessionBase {
         while (log_m > 0 && (g.nb >> log_m) < 64) log_m--;
         const uint32_t max_nb = std::max(g.nb, g.nb_top);
         const uint32_t chunks = (max_nb + (1u << log_m) - 1) >> log_m;
-        uint32_t *partials = nullptr, *window_sums = nullptr;
+        uint32_t *partials = nullptr, *partials2 = nullptr, *window_sums = nullptr;
         if (int rc = arena.alloc(&partials, (size_t)g.W * chunks * 4 * L * 4)) return rc;
+        if (int rc = arena.alloc(&partials2, (size_t)g.W * 32 * 4 * L * 4)) return rc;
         if (int rc = arena.alloc(&window_sums, (size_t)g.W * 4 * L * 4)) return rc;
-        if (int rc = MsmRedLaunch<C>::reduce(buckets, g, log_m, chunks, partials, window_sums, st)) return rc;
+        if (int rc = MsmRedLaunch<C>::reduce(buckets, g, log_m, chunks, partials, partials2, window_sums, st)) return rc;
         AB_CUDA(cudaEventRecord(e_red, st));
         if (int rc = MsmRedLaunch<C>::combine(window_sums, g.W, g.c, d_out, st)) return rc;
         AB_CUDA(cudaEventRecord(e_end, st));

@@ -87,7 +87,9 @@ template <class C> struct MsmAccLaunch {
     static int merge(uint32_t *buckets, const uint32_t *extra, uint32_t nb, cudaStream_t st);
 };
 template <class C> struct MsmRedLaunch {
-    static int reduce(const uint32_t *buckets, MsmGeom g, int log_m, uint32_t chunks, uint32_t *partials, uint32_t *window_sums, cudaStream_t st);
+    // partials: W * chunks buckets of scratch; partials2: W * 32
+    static int reduce(const uint32_t *buckets, MsmGeom g, int log_m, uint32_t chunks, uint32_t *partials, uint32_t *partials2, uint32_t *window_sums,
+                      cudaStream_t st);
     static int combine(const uint32_t *window_sums, int W, int c, uint32_t *out, cudaStream_t st);
     static int sum_or_affine(bool to_affine, const uint32_t *d_in, size_t k, uint32_t *d_out, cudaStream_t st);
 };

@@ -59,6 +59,7 @@ template <class F> __device__ __forceinline__ void shfl_limbs(uint32_t *r, const
 template <class F> __device__ __noinline__ void block_inverse(uint32_t *inv, const uint32_t *run, uint32_t *sm) {
     constexpr int L = F::L;
     const int tid = threadIdx.x, lane = tid & 31;
+    __syncthreads();   // `sm` may alias staging strips that slower warps of the block are still reading
 #pragma unroll
     for (int i = 0; i < L; i++) sm[i * 128 + tid] = run[i];
     __syncthreads();
@@ -238,16 +239,23 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add_kernel(const uint32_t 
 //   * slot -> input-pair mapping comes from `pairmap` (msm_pairmap_kernel), not from a per-thread bucket walk.
 // Same arithmetic, same degenerate-pair handling and same output layout as msm_pair_add_kernel.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+// CA = true: cp.async.ca (allocates in L1: the three 16-byte chunks of a 48-byte coordinate, and x then y of a point, hit the line
+// the first chunk brought in); CA = false: cp.async.cg (L2 only)
+template <bool CA> __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
+    if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+#ifndef AB_PAIR_CPASYNC_CA
+#define AB_PAIR_CPASYNC_CA 1
+#endif
+static constexpr bool kPairCpAsyncCA = AB_PAIR_CPASYNC_CA != 0;
 // per-thread strip: element e, 16-byte chunk j of thread t lives at uint4 index (e*(L/4) + j)*128 + t (conflict-free)
-template <int L> __device__ __forceinline__ void strip_fetch(uint32_t sbase, int e, const uint32_t *g) {
+template <int L, bool CA> __device__ __forceinline__ void strip_fetch(uint32_t sbase, int e, const uint32_t *g) {
 #pragma unroll
-    for (int j = 0; j < L / 4; j++) cp_async16(sbase + ((uint32_t)((e * (L / 4) + j) * 128 + threadIdx.x) << 4), g + 4 * j);
+    for (int j = 0; j < L / 4; j++) cp_async16<CA>(sbase + ((uint32_t)((e * (L / 4) + j) * 128 + threadIdx.x) << 4), g + 4 * j);
 }
 template <int L> __device__ __forceinline__ void strip_read(uint32_t *r, const uint4 *sm, int e) {
 #pragma unroll
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
     m_c = __ldg(pairmap + p0);
     if (FIRST) { e1_c = __ldg(src + (m_c & 0x7fffffffu)); if (m_c >> 31) e2_c = __ldg(src + (m_c & 0x7fffffffu) + 1); }
     // (forward uses strip elements {0,2} for even slots and {1,3} for odd ones: a true double buffer)
-    if (m_c >> 31) { strip_fetch<L>(sbase, 0, point(m_c & 0x7fffffffu, e1_c)); strip_fetch<L>(sbase, 2, point((m_c & 0x7fffffffu) + 1, e2_c)); }
+    if (m_c >> 31) { strip_fetch<L, kPairCpAsyncCA>(sbase, 0, point(m_c & 0x7fffffffu, e1_c)); strip_fetch<L, kPairCpAsyncCA>(sbase, 2, point((m_c & 0x7fffffffu) + 1, e2_c)); }
     cp_async_commit();
     if (cnt > 1) {
         m_n = __ldg(pairmap + p0 + 32);
@@ -304,8 +312,8 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
         const int eb = (int)(i & 1);
         if (has2) { strip_read<L>(x1, strip, eb); strip_read<L>(x2, strip, 2 + eb); }
         if (i + 1 < cnt && (m_n >> 31)) {
-            strip_fetch<L>(sbase, 1 - eb, point(m_n & 0x7fffffffu, e1_n));
-            strip_fetch<L>(sbase, 3 - eb, point((m_n & 0x7fffffffu) + 1, e2_n));
+            strip_fetch<L, kPairCpAsyncCA>(sbase, 1 - eb, point(m_n & 0x7fffffffu, e1_n));
+            strip_fetch<L, kPairCpAsyncCA>(sbase, 3 - eb, point((m_n & 0x7fffffffu) + 1, e2_n));
         }
         cp_async_commit();
         uint32_t e1_nn = 0, e2_nn = 0, m_n3 = 0;
@@ -338,14 +346,14 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
     auto fetch_bwd = [&](uint32_t m, uint32_t e1, uint32_t e2, uint32_t i) {   // operands of slot i and the prefix parked in slot i-1
         const uint32_t k = m & 0x7fffffffu;
         const uint32_t *a = point(k, e1);
-        strip_fetch<L>(sbase, 0, a);
-        strip_fetch<L>(sbase, 1, a + L);
+        strip_fetch<L, kPairCpAsyncCA>(sbase, 0, a);
+        strip_fetch<L, kPairCpAsyncCA>(sbase, 1, a + L);
         if (m >> 31) {
             const uint32_t *b = point(k + 1, e2);
-            strip_fetch<L>(sbase, 2, b);
-            strip_fetch<L>(sbase, 3, b + L);
+            strip_fetch<L, kPairCpAsyncCA>(sbase, 2, b);
+            strip_fetch<L, kPairCpAsyncCA>(sbase, 3, b + L);
         }
-        if (i > 0) strip_fetch<L>(sbase, 4, out + (size_t)(p0 + 32 * (i - 1)) * (2 * L));
+        if (i > 0) strip_fetch<L, kPairCpAsyncCA>(sbase, 4, out + (size_t)(p0 + 32 * (i - 1)) * (2 * L));
     };
     m_c = __ldg(pairmap + p0 + 32 * (cnt - 1));
     e1_c = e2_c = e1_n = e2_n = 0;

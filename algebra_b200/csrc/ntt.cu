@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <tuple>
 #include <vector>
@@ -440,8 +441,19 @@ struct NttPlan {
     uint32_t scale[8];  // 1/n (Montgomery) for the inverse, ONE otherwise
     bool inverse = false;
 };
+// Plans are shared_ptr-owned: a transform keeps its plan alive while it runs, so a concurrent b200_clear_cache (or an LRU eviction)
+// only drops the cache's reference; the tables are freed when the last user lets go (cudaFree waits for kernels still reading them).
+// The cache is bounded: least-recently-used plans are evicted once the cached tables exceed kPlanCacheBytes.
+struct NttPlanOwner {
+    NttPlan p;
+    size_t bytes = 0;
+    uint64_t last_use = 0;
+    ~NttPlanOwner();
+};
+static constexpr size_t kPlanCacheBytes = (size_t)6 << 30;
 static std::mutex g_plan_mutex;
-static std::map<std::tuple<int, int, int, int>, NttPlan> g_plans;
+static std::map<std::tuple<int, int, int, int>, std::shared_ptr<NttPlanOwner>> g_plans;
+static uint64_t g_plan_clock = 0;
 
 template <class P> static void host_root_of_unity(uint32_t *g, int log_n) {
     // get_root_of_unity, ff/src/fields/fft_friendly.rs:66-82
@@ -518,16 +530,20 @@ static void free_plan(NttPlan &pl) {
     for (auto &p : pl.tw_seg)
         if (p) cudaFree(p);
 }
+NttPlanOwner::~NttPlanOwner() { free_plan(p); }
 
 int ntt_clear_cache() {
-    std::lock_guard<std::mutex> lk(g_plan_mutex);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    for (auto it = g_plans.begin(); it != g_plans.end();) {
-        if (std::get<0>(it->first) == dev) {
-            free_plan(it->second);
-            it = g_plans.erase(it);
-        } else ++it;
+    std::vector<std::shared_ptr<NttPlanOwner>> dropped;   // destroyed (and their tables freed) outside the lock
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mutex);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        for (auto it = g_plans.begin(); it != g_plans.end();) {
+            if (std::get<0>(it->first) == dev) {
+                dropped.push_back(it->second);
+                it = g_plans.erase(it);
+            } else ++it;
+        }
     }
     return 0;
 }
@@ -613,19 +629,35 @@ template <class P> static int ntt_run(int field, uint4 *d_data, int log_n, bool 
 
     int dev = 0;
     AB_CUDA(cudaGetDevice(&dev));
-    NttPlan plan;
+    std::shared_ptr<NttPlanOwner> owner;   // keeps the tables alive for the duration of this transform
+    std::vector<std::shared_ptr<NttPlanOwner>> evicted;
     {
         std::lock_guard<std::mutex> lk(g_plan_mutex);
         auto key = std::make_tuple(dev, field, log_n, (int)inverse);
         auto it = g_plans.find(key);
         if (it == g_plans.end()) {
-            NttPlan pl;
-            int rc = build_plan<P>(pl, log_n, inverse, st);
-            if (rc) { free_plan(pl); return rc; }
-            it = g_plans.emplace(key, pl).first;
+            auto fresh = std::make_shared<NttPlanOwner>();
+            int rc = build_plan<P>(fresh->p, log_n, inverse, st);
+            if (rc) return rc;
+            int ls = log_n;
+            for (int t = 0; t + 1 < fresh->p.m; t++) { fresh->bytes += (size_t)32 << ls; ls -= fresh->p.radix_log[t]; }
+            it = g_plans.emplace(key, fresh).first;
+            size_t total = 0;
+            for (auto &kv : g_plans) total += kv.second->bytes;
+            while (total > kPlanCacheBytes && g_plans.size() > 1) {   // evict least recently used (never the one just built)
+                auto victim = g_plans.end();
+                for (auto jt = g_plans.begin(); jt != g_plans.end(); ++jt)
+                    if (jt != it && (victim == g_plans.end() || jt->second->last_use < victim->second->last_use)) victim = jt;
+                if (victim == g_plans.end()) break;
+                total -= victim->second->bytes;
+                evicted.push_back(victim->second);
+                g_plans.erase(victim);
+            }
         }
-        plan = it->second;
+        owner = it->second;
+        owner->last_use = ++g_plan_clock;
     }
+    const NttPlan &plan = owner->p;
     LimbArg<8> one_arg, g_arg;
     for (int i = 0; i < 8; i++) one_arg.v[i] = P::ONE(i);
 

@@ -55,9 +55,9 @@ template <class F> __global__ void fp2_op_kernel(int op, const uint32_t *a, cons
     store_limbs<L>(out + i * L, r);
 }
 
-template <class P> __global__ void ec_op_kernel(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
-    using E = Ec<Fp<P>>;
-    constexpr int L = P::L;
+template <class FT> __global__ void ec_op_kernel(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
+    using E = Ec<FT>;
+    constexpr int L = FT::L;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     typename E::B x, y;
@@ -127,8 +127,9 @@ int ec_op_dispatch(int curve, int op, const void *a, const void *b, void *out, s
     if ((op == 0 || op == 1 || op == 2 || op == 6) && !b) { set_last_error("second operand required"); return B200_EINVAL; }
     if (n == 0) return 0;
     unsigned blocks = (unsigned)((n + 63) / 64);
-    if (curve == B200_CURVE_BLS12_381) ec_op_kernel<BlsFq><<<blocks, 64, 0, st>>>(op, (const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out, n);
-    else if (curve == B200_CURVE_BN254) ec_op_kernel<BnFq><<<blocks, 64, 0, st>>>(op, (const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out, n);
+    if (curve == B200_CURVE_BLS12_381) ec_op_kernel<Fp<BlsFq>><<<blocks, 64, 0, st>>>(op, (const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out, n);
+    else if (curve == B200_CURVE_BN254) ec_op_kernel<Fp<BnFq>><<<blocks, 64, 0, st>>>(op, (const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out, n);
+    else if (curve == B200_CURVE_BLS12_381_G2) ec_op_kernel<Fp2<BlsFq>><<<blocks, 64, 0, st>>>(op, (const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out, n);
     else { set_last_error("unknown curve id"); return B200_EINVAL; }
     AB_LAUNCHED();
     return 0;

@@ -109,3 +109,53 @@ def test_ec_ops(lib, cid):
     a3 = run("jac_to_affine", j3)
     want = [cv.add(cv.add(pts[i], pts[(i - 1) % n]), cv.neg(pts[(i - 2) % n])) for i in range(n)]
     assert cv.decode_affine(a3) == want
+
+
+def test_g2_ec_ops_vs_oracle(lib):
+    """ec.cuh instantiated over Fp2 (the G2 MSM's point arithmetic): XYZZ mixed add / add / double, Jacobian add / double and the
+    conversions, run on the host through the PTX emulation and compared (as affine points) with the G2 oracle, which is pinned on
+    the reference's i*G2 table."""
+    g2 = O.BLS12_381_G2
+    fq = O.BLS12_381_FQ
+    rnd = random.Random(77)
+    ks = [rnd.randrange(1, 1 << 40) for _ in range(12)]
+    P = [g2.mul(g2.G, k) for k in ks]
+    Q = [g2.mul(g2.G, rnd.randrange(1, 1 << 40)) for _ in ks]
+    Q[3] = P[3]                      # doubling branch
+    Q[4] = g2.neg(P[4])              # cancellation
+    Q[5] = None                      # + identity
+
+    def enc2(c):                     # Fq2 -> 12 u64 Montgomery limbs
+        return np.array(fq.limbs(fq.to_mont(c[0])) + fq.limbs(fq.to_mont(c[1])), dtype=np.uint64)
+
+    def xyzz(Pt):                    # affine -> bucket (x, y, 1, 1); identity -> (1, 1, 0, 0)
+        if Pt is None:
+            return np.concatenate([enc2((1, 0)), enc2((1, 0)), enc2((0, 0)), enc2((0, 0))])
+        return np.concatenate([enc2(Pt[0]), enc2(Pt[1]), enc2((1, 0)), enc2((1, 0))])
+
+    def run(op, a, b, wo):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64) if b is not None else a
+        out = np.zeros((a.shape[0], wo * 12), dtype=np.uint64)
+        assert lib.selftest_ec_op(2, op, _p(a.view(np.uint32)), _p(b.view(np.uint32)), _p(out.view(np.uint32)), a.shape[0]) == 0
+        return out
+
+    def xyzz_affine(rows):           # bucket -> jacobian (op 4) -> affine (op 5)
+        return g2.decode_affine(run(5, run(4, rows, None, 3), None, 2))
+
+    B = np.stack([xyzz(p) for p in P])
+    Aq = g2.encode_affine(Q)
+    assert xyzz_affine(run(0, B, Aq, 4)) == [g2.add(p, q) for p, q in zip(P, Q)]              # Bucket += Affine
+    assert xyzz_affine(run(1, B, Aq, 4)) == [g2.add(p, g2.neg(q)) for p, q in zip(P, Q)]      # Bucket -= Affine
+    B2 = run(0, np.stack([xyzz(None)] * len(Q)), Aq, 4)                                        # identity bucket += Q
+    assert xyzz_affine(B2) == Q
+    S = run(0, B, g2.encode_affine(P[1:] + P[:1]), 4)                                          # non-trivial zz, zzz
+    T = run(0, np.stack([xyzz(q) for q in Q]), g2.encode_affine(P[2:] + P[:2]), 4)
+    sa, ta = xyzz_affine(S), xyzz_affine(T)
+    assert xyzz_affine(run(2, S, T, 4)) == [g2.add(x, y) for x, y in zip(sa, ta)]              # Bucket += &Bucket
+    assert xyzz_affine(run(2, S, S, 4)) == [g2.add(x, x) for x in sa]                          # ... doubling branch
+    assert xyzz_affine(run(3, S, None, 4)) == [g2.add(x, x) for x in sa]                       # double_in_place
+    J, K = run(4, S, None, 3), run(4, T, None, 3)
+    assert g2.decode_affine(run(5, run(6, J, K, 3), None, 2)) == [g2.add(x, y) for x, y in zip(sa, ta)]   # Projective += Projective
+    assert g2.decode_affine(run(5, run(6, J, J, 3), None, 2)) == [g2.add(x, x) for x in sa]
+    assert g2.decode_affine(run(5, run(7, J, None, 3), None, 2)) == [g2.add(x, x) for x in sa]             # double_in_place

@@ -27,9 +27,9 @@ template <class P> static int fp_op(int op, const uint32_t *a, const uint32_t *b
     }
     return 0;
 }
-template <class P> static int ec_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
-    constexpr int L = P::L;
-    using E = Ec<Fp<P>>;
+template <class FT> static int ec_op(int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
+    constexpr int L = FT::L;
+    using E = Ec<FT>;
     for (size_t i = 0; i < n; i++) {
         typename E::B x, y; typename E::J j, k;
         switch (op) {
@@ -57,5 +57,6 @@ extern "C" int selftest_fp_op(int field, int op, const uint32_t *a, const uint32
     return 1;
 }
 extern "C" int selftest_ec_op(int curve, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
-    return curve == 0 ? ec_op<BlsFq>(op, a, b, out, n) : curve == 1 ? ec_op<BnFq>(op, a, b, out, n) : 1;
+    return curve == 0 ? ec_op<Fp<BlsFq>>(op, a, b, out, n) : curve == 1 ? ec_op<Fp<BnFq>>(op, a, b, out, n)
+         : curve == 2 ? ec_op<Fp2<BlsFq>>(op, a, b, out, n) : 1;   // 2 = G2 of BLS12-381 (coordinates in Fq2)
 }

@@ -251,8 +251,15 @@ template <class P> struct Fp {
         }
         // m = T[0] * (-p^-1) mod 2^32; for moduli with p = 1 (mod 2^32) (BLS12-381 Fr) that is simply -T[0]
         const uint32_t m = (P::INV32 == 0xffffffffu) ? (0u - ev[0]) : ev[0] * P::INV32;
-        od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
-        od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
+        if (P::MOD(1) == 0xffffffffu) {  // p[1] = 2^32 - 1 (BLS12-381 Fr): m*p[1] = (m << 32) - m — four adds instead of a wide MAD
+            const uint32_t plo = ptx::sub_cc(0u, m);   // low word of the product; borrow <=> m != 0
+            const uint32_t phi = ptx::subc(m, 0u);     // high word = m - (m != 0)
+            od[0] = ptx::add_cc(od[0], plo);
+            od[1] = ptx::addc_cc(od[1], phi);
+        } else {
+            od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
+            od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
+        }
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             od[j] = ptx::madc_lo_cc(P::MOD(j + 1), m, od[j]);
@@ -375,8 +382,15 @@ template <class P> struct Fp {
             od[L - 1] = ptx::addc(0u, 0u);
         }
         const uint32_t m = (P::INV32 == 0xffffffffu) ? (0u - ev[0]) : ev[0] * P::INV32;
-        od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
-        od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
+        if (P::MOD(1) == 0xffffffffu) {  // p[1] = 2^32 - 1 (BLS12-381 Fr): m*p[1] = (m << 32) - m — four adds instead of a wide MAD
+            const uint32_t plo = ptx::sub_cc(0u, m);   // low word of the product; borrow <=> m != 0
+            const uint32_t phi = ptx::subc(m, 0u);     // high word = m - (m != 0)
+            od[0] = ptx::add_cc(od[0], plo);
+            od[1] = ptx::addc_cc(od[1], phi);
+        } else {
+            od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
+            od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
+        }
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             od[j] = ptx::madc_lo_cc(P::MOD(j + 1), m, od[j]);

@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(256) msm_pairmap_kernel(const uint32_t *__rest
 // knobs without a public setter, from environment variables read ONCE per process (never on the call path).
 struct EnvKnobs {
     int pair_variant = 2;                 // levels >= 2: 1 = thread-contiguous batches, 2 = warp-interleaved + cp.async staging
-    int pair_variant_l1 = 1;              // level 1 (random gathers from the bases): measured 141.7 ms (1) vs 171.1 ms (2) @2^26
+    int pair_variant_l1 = 2;              // level 1 (random gathers from the bases).  Measured @2^26, level-1 kernel: generation 1 141.7 ms;
+                                          // generation 2 with cp.async.cg (L2 only: every 16-byte chunk of a point is its own L2 request)
+                                          // 171.1 ms; generation 2 with cp.async.ca (chunks 2..6 of a point hit the L1 line) ~100 ms —
+                                          // accumulation phase 285 -> 243 ms, whole step 333 -> 291 ms
     double level_budget_bytes = 72e9;     // scratch allowed for the affine level arrays (window groups are sized to fit); also capped
                                           // by 60 % of the free device memory at the start of the call.  Measured @2^26 (accumulation
                                           // phase): no groups (63 GB of levels) 280 ms, 2 groups (48 GB budget) 296 ms, 4 groups (24 GB) 306 ms,
@@ -177,7 +180,7 @@ struct EnvKnobs {
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
     EnvKnobs() {
         if (const char *e = getenv("B200_MSM_PAIR_VARIANT")) pair_variant = atoi(e) == 1 ? 1 : 2;
-        if (const char *e = getenv("B200_MSM_PAIR_VARIANT_L1")) pair_variant_l1 = atoi(e) == 2 ? 2 : 1;
+        if (const char *e = getenv("B200_MSM_PAIR_VARIANT_L1")) pair_variant_l1 = atoi(e) == 1 ? 1 : 2;
         if (const char *e = getenv("B200_MSM_LEVEL_BUDGET_GB")) { double v = atof(e); if (v > 0.01) level_budget_bytes = v * 1e9; }
         if (const char *e = getenv("B200_MSM_SHARED_INV")) shared_inv = atoi(e) != 0;
         min_batch = shared_inv ? 96 : 256;   // overhead per addition: 590/(4*batch) multiplications shared, 570/batch per thread

@@ -254,14 +254,20 @@ template <class P, bool LAST> __device__ __forceinline__ void radix4_dif(uint32_
     if (LAST) limbs_copy<8>(x[3], t); else F::mul(x[3], t, w);
 }
 
+// kNtt2Buffers tile buffers of 8 KiB per warp.  Measured on B200 @2^24: 2 buffers / 3 blocks of 4 warps per SM (142 registers, both
+// final radix-4 groups held in registers) 5.22 ms — 12 warps per SM leave the integer pipe idle 40 % of the time; 1 buffer / 6 blocks
+// (<= 85 registers, final groups one after the other, the next tile requested when the second group has been read) is the shipped form.
+static constexpr int kNtt2Buffers = 1, kNtt2BlocksPerSm = 6;
+static constexpr size_t kNtt2SmemBytes = (size_t)4 * kNtt2Buffers * 8192 + 64;
+
 template <class P>
-__global__ void __launch_bounds__(128, 3) ntt2_pass_kernel(const __grid_constant__ CUtensorMap tmap, const uint4 *__restrict__ in, uint4 *__restrict__ out,
-                                                           Ntt2Params pp) {
+__global__ void __launch_bounds__(128, kNtt2BlocksPerSm) ntt2_pass_kernel(const __grid_constant__ CUtensorMap tmap, const uint4 *__restrict__ in,
+                                                                          uint4 *__restrict__ out, Ntt2Params pp) {
     using F = Fp<P>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4 *buf0 = reinterpret_cast<uint4 *>(smem_raw + (size_t)warp * 16384);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 4 * 16384) + warp * 2;
+    uint4 *buf0 = reinterpret_cast<uint4 *>(smem_raw + (size_t)warp * kNtt2Buffers * 8192);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)4 * kNtt2Buffers * 8192) + warp * 2;
     const int r = pp.r, A = 1 << r, logC = pp.logC, C = 1 << logC;
     const int logB = pp.log_seg - r, logA1 = pp.radix_log[0];
     const uint32_t nwarps = gridDim.x * 4, wid = blockIdx.x * 4 + warp;
@@ -280,20 +286,19 @@ __global__ void __launch_bounds__(128, 3) ntt2_pass_kernel(const __grid_constant
             tma_load_3d(dst, &tmap, (int)(cg << (logC + 2)), 0, (int)sigma, &bars[stage]);
         } else {
             // tile = qg * A1 + g: C consecutive sub-transforms (q = qg*C + rho) of input row block g -> 256 contiguous elements
-            const uint32_t g = pp.m > 1 ? (tile & ((1u << logA1) - 1)) : 0, qg = pp.m > 1 ? (tile >> logA1) : tile;
+            const uint32_t g = tile & ((1u << logA1) - 1), qg = tile >> logA1;
             const size_t pos = ((size_t)g << (pp.log_n - logA1)) + ((size_t)qg << 8);
             bulk_load_1d(dst, in + 2 * pos, 8192, &bars[stage]);
         }
     };
-    if (lane == 0) {
-        if (wid < pp.tiles) request(wid, 0);
-        if (wid + nwarps < pp.tiles) request(wid + nwarps, 1);
-    }
+    if (lane == 0)
+        for (int b = 0; b < kNtt2Buffers; b++)
+            if (wid + (size_t)b * nwarps < pp.tiles) request(wid + b * nwarps, b);
     uint32_t it = 0;
     for (uint32_t tile = wid; tile < pp.tiles; tile += nwarps, it++) {
-        const int stage = it & 1;
+        const int stage = it % kNtt2Buffers;
         uint4 *buf = buf0 + stage * 512;
-        mbar_wait(&bars[stage], (it >> 1) & 1);
+        mbar_wait(&bars[stage], (it / kNtt2Buffers) & 1);
         // element (row a, column c) of the tile: non-last layout [a][c] (TMA box), last layout [c][a] (contiguous runs)
         auto slot = [&](int a, int c) { return pp.is_last ? ((c << r) + a) : ((a << logC) + c); };
         int stages_left = r;
@@ -335,55 +340,49 @@ __global__ void __launch_bounds__(128, 3) ntt2_pass_kernel(const __grid_constant
             }
             __syncwarp();
         }
-        // last two stages (h = 1) in registers for both groups of the lane, then the buffer is free for the next request
-        uint32_t z[2][4][8];
-        int zc[2], za[2];
-#pragma unroll
+        // last two stages (h = 1) in registers, one group of four rows at a time; results go straight to global memory, so once the
+        // second group has been read the buffer is free and the next tile is requested
+#pragma unroll 1
         for (int k = 0; k < 2; k++) {
             const int gam = lane + 32 * k;
-            int c, rest;
-            if (pp.is_last) { c = gam >> (r - 2); rest = gam & ((A >> 2) - 1); }
-            else { c = gam & (C - 1); rest = gam >> logC; }
-            zc[k] = c; za[k] = rest << 2;
+            int zc, rest;
+            if (pp.is_last) { zc = gam >> (r - 2); rest = gam & ((A >> 2) - 1); }
+            else { zc = gam & (C - 1); rest = gam >> logC; }
+            const int za = rest << 2;
+            uint32_t z[4][8];
 #pragma unroll
-            for (int e = 0; e < 4; e++) ld_elem(z[k][e], buf + 2 * slot(za[k] + e, c));
-        }
-        __syncwarp();
-        if (lane == 0 && tile + 2 * (size_t)nwarps < pp.tiles) request(tile + 2 * nwarps, stage);
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            radix4_dif<P, true>(z[k], pp.tw_small, 0, 1);
+            for (int e = 0; e < 4; e++) ld_elem(z[e], buf + 2 * slot(za + e, zc));
+            if (k == 1) {
+                __syncwarp();
+                if (lane == 0 && tile + (size_t)kNtt2Buffers * nwarps < pp.tiles) request(tile + kNtt2Buffers * nwarps, stage);
+            }
+            radix4_dif<P, true>(z, pp.tw_small, 0, 1);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const size_t iA = __brev((unsigned)(za[k] + e)) >> (32 - r);   // row a holds sub-transform output bitrev_r(a)
+                const size_t iA = __brev((unsigned)(za + e)) >> (32 - r);   // row a holds sub-transform output bitrev_r(a)
                 size_t pos;
                 if (!pp.is_last) {
                     const int log_cg = logB - logC;
                     const size_t cg = tile & ((1u << log_cg) - 1), sigma = tile >> log_cg;
-                    const size_t off = (iA << logB) + (cg << logC) + zc[k];
+                    const size_t off = (iA << logB) + (cg << logC) + zc;
                     pos = (sigma << pp.log_seg) + off;
                     uint32_t w[8];
                     ldg_elem(w, pp.tw_seg + 2 * off);
-                    F::mul(z[k][e], z[k][e], w);
+                    F::mul(z[e], z[e], w);
                 } else {
-                    if (pp.has_scale) F::mul(z[k][e], z[k][e], pp.scale);
-                    if (pp.m > 1) {
-                        const size_t g = tile & ((1u << logA1) - 1), q = ((size_t)(tile >> logA1) << logC) + zc[k];
-                        // position digits (i1 | i2 .. i_{m-1} | i_m)  ->  index i1 + A1*(i2 + A2*(... + A_{m-1}*i_m))
-                        size_t rev = 0, rem = q;
-                        int shift = 0, pv = pp.log_n - logA1 - r;
-                        for (int d = 1; d < pp.m - 1; d++) {
-                            pv -= pp.radix_log[d];
-                            rev += (rem >> pv) << shift;
-                            rem &= ((size_t)1 << pv) - 1;
-                            shift += pp.radix_log[d];
-                        }
-                        pos = g + ((rev + (iA << shift)) << logA1);
-                    } else {
-                        pos = iA;   // (single-pass plans use the first-generation kernel)
+                    const size_t g = tile & ((1u << logA1) - 1), q = ((size_t)(tile >> logA1) << logC) + zc;
+                    // position digits (i1 | i2 .. i_{m-1} | i_m)  ->  index i1 + A1*(i2 + A2*(... + A_{m-1}*i_m))
+                    size_t rev = 0, rem = q;
+                    int shift = 0, pv = pp.log_n - logA1 - r;
+                    for (int d = 1; d < pp.m - 1; d++) {
+                        pv -= pp.radix_log[d];
+                        rev += (rem >> pv) << shift;
+                        rem &= ((size_t)1 << pv) - 1;
+                        shift += pp.radix_log[d];
                     }
+                    pos = g + ((rev + (iA << shift)) << logA1);
                 }
-                st_elem(out + 2 * pos, z[k][e]);
+                st_elem(out + 2 * pos, z[e]);
             }
         }
     }
@@ -598,9 +597,9 @@ template <class P> static int ntt2_launch_pass(const NttPlan &plan, int t, int l
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = 4 * 16384 + 64;
+    const size_t smem = kNtt2SmemBytes;
     AB_CUDA(cudaFuncSetAttribute(ntt2_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)std::min<size_t>((size_t)sms * 3, (pp.tiles + 3) / 4);
+    const unsigned blocks = (unsigned)std::min<size_t>((size_t)sms * kNtt2BlocksPerSm, (pp.tiles + 3) / 4);
     ntt2_pass_kernel<P><<<blocks, 128, smem, st>>>(map, src, dst, pp);
     AB_LAUNCHED();
     (void)inverse;

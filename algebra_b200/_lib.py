@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libalgebra_b200.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libalgebra_b200.so")   # (override: build-variant debugging)
 
 EINVAL, ETOOLARGE, ENOMEM = -1, -2, -3
 SCALARS_FR_MONT, SCALARS_BIGINT, SCALARS_U8, SCALARS_U16, SCALARS_U32, SCALARS_U64 = range(6)

@@ -104,7 +104,16 @@ template <class FT> struct Ec {
     }
 
     // bucket.rs:112-146
+#if defined(__CUDACC__) && defined(AB_EC_NOINLINE_WIDE)
+    static __host__ __device__ __noinline__ void xyzz_dbl_call(B &b) { xyzz_dbl_impl(b); }
     static AB_HD void xyzz_dbl(B &b) {
+        if (L > 12) xyzz_dbl_call(b);
+        else xyzz_dbl_impl(b);
+    }
+#else
+    static AB_HD void xyzz_dbl(B &b) { xyzz_dbl_impl(b); }
+#endif
+    static AB_HD void xyzz_dbl_impl(B &b) {
         uint32_t u[L], v[L], w[L], s[L], m[L], t[L];
         F::dbl(u, b.y);
         F::sqr(v, u);
@@ -125,7 +134,16 @@ template <class FT> struct Ec {
     }
 
     // bucket.rs:256-337
+#if defined(__CUDACC__) && defined(AB_EC_NOINLINE_WIDE)
+    static __host__ __device__ __noinline__ void xyzz_add_call(B &a, const B &o) { xyzz_add_impl(a, o); }
     static AB_HD void xyzz_add(B &a, const B &o) {
+        if (L > 12) xyzz_add_call(a, o);
+        else xyzz_add_impl(a, o);
+    }
+#else
+    static AB_HD void xyzz_add(B &a, const B &o) { xyzz_add_impl(a, o); }
+#endif
+    static AB_HD void xyzz_add_impl(B &a, const B &o) {
         if (xyzz_is_zero(a)) { a = o; return; }
         if (xyzz_is_zero(o)) return;
         uint32_t u1[L], u2[L], s1[L], s2[L];

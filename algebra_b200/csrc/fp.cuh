@@ -158,8 +158,35 @@ template <int L> AB_HD bool limbs_eq(const uint32_t *a, const uint32_t *b) {
     return o == 0;
 }
 
+// The trivial multipliers 1 and 2^32-1 of "Montgomery-friendly" moduli (BLS12-381 Fr = ...ffffffff00000001, INV = -1) are read
+// from constant memory instead of being immediates, so that ptxas keeps every (mad.lo.cc, madc.hi.cc) pair a fused
+// IMAD.WIDE.U32(.X): with strength-reduced forms (m = -T[0], m*1 -> add, m*(2^32-1) -> shift/sub) the carry chains start with
+// IADD3s and the remaining pairs of the row come out as IMAD.X + IMAD.HI.U32.X — two issues on the multiplier pipe instead of
+// one.  Round 1 shipped that form: 66 fused + 48 unfused pairs per Fr multiplication; now 123 fused (cuobjdump counts in
+// profiles/r02_sass_opcode_counts.txt).
+#ifdef __CUDACC__
+static __constant__ uint32_t ab_opaque_words[2] = {1u, 0xffffffffu};
+#endif
+
 template <class P> struct Fp {
     static constexpr int L = P::L;
+    // -p^-1 mod 2^32.  For p = 1 (mod 2^32) this is 2^32-1 and m = -T[0]; written as a negation, ptxas stops fusing ALL m*p[j]
+    // products of the row (IMAD.X + IMAD.HI.U32.X pairs instead of IMAD.WIDE.U32.X: 48 of 115 per multiplication for BLS12-381
+    // Fr), so the multiplier stays an opaque constant-memory word and m is a real product.
+    static AB_HD uint32_t inv_word() {
+#ifdef __CUDA_ARCH__
+        if (P::INV32 == 0xffffffffu) return ab_opaque_words[1];
+#endif
+        return P::INV32;
+    }
+    // modulus word I as a multiplier operand
+    template <int I> static AB_HD uint32_t mod_word() {
+#ifdef __CUDA_ARCH__
+        if (P::MOD(I) == 1u) return ab_opaque_words[0];
+        if (P::MOD(I) == 0xffffffffu) return ab_opaque_words[1];
+#endif
+        return P::MOD(I);
+    }
 
     // r = (a >= p) ? a - p : a        (`subtract_modulus`, ff/src/fields/models/fp/mod.rs:140-155)
     static AB_HD void reduce_once(uint32_t *a) {
@@ -250,28 +277,16 @@ template <class P> struct Fp {
             od[L - 1] = ptx::addc(od[L - 1], 0u);
         }
         // m = T[0] * (-p^-1) mod 2^32; for moduli with p = 1 (mod 2^32) (BLS12-381 Fr) that is simply -T[0]
-        const uint32_t m = (P::INV32 == 0xffffffffu) ? (0u - ev[0]) : ev[0] * P::INV32;
-        if (P::MOD(1) == 0xffffffffu) {  // p[1] = 2^32 - 1 (BLS12-381 Fr): m*p[1] = (m << 32) - m — four adds instead of a wide MAD
-            const uint32_t plo = ptx::sub_cc(0u, m);   // low word of the product; borrow <=> m != 0
-            const uint32_t phi = ptx::subc(m, 0u);     // high word = m - (m != 0)
-            od[0] = ptx::add_cc(od[0], plo);
-            od[1] = ptx::addc_cc(od[1], phi);
-        } else {
-            od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
-            od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
-        }
+        const uint32_t m = ev[0] * inv_word();
+        od[0] = ptx::mad_lo_cc(mod_word<1>(), m, od[0]);
+        od[1] = ptx::madc_hi_cc(mod_word<1>(), m, od[1]);
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             od[j] = ptx::madc_lo_cc(P::MOD(j + 1), m, od[j]);
             od[j + 1] = ptx::madc_hi_cc(P::MOD(j + 1), m, od[j + 1]);
         }
-        if (P::MOD(0) == 1u) {  // p[0] = 1: the product m*p[0] is m itself — an add instead of a wide MAD
-            ev[0] = ptx::add_cc(ev[0], m);
-            ev[1] = ptx::addc_cc(ev[1], 0u);
-        } else {
-            ev[0] = ptx::mad_lo_cc(P::MOD(0), m, ev[0]);
-            ev[1] = ptx::madc_hi_cc(P::MOD(0), m, ev[1]);
-        }
+        ev[0] = ptx::mad_lo_cc(mod_word<0>(), m, ev[0]);
+        ev[1] = ptx::madc_hi_cc(mod_word<0>(), m, ev[1]);
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             ev[j] = ptx::madc_lo_cc(P::MOD(j), m, ev[j]);
@@ -381,28 +396,16 @@ template <class P> struct Fp {
             od[L - 2] = ptx::addc_cc(hi_word, 0u);
             od[L - 1] = ptx::addc(0u, 0u);
         }
-        const uint32_t m = (P::INV32 == 0xffffffffu) ? (0u - ev[0]) : ev[0] * P::INV32;
-        if (P::MOD(1) == 0xffffffffu) {  // p[1] = 2^32 - 1 (BLS12-381 Fr): m*p[1] = (m << 32) - m — four adds instead of a wide MAD
-            const uint32_t plo = ptx::sub_cc(0u, m);   // low word of the product; borrow <=> m != 0
-            const uint32_t phi = ptx::subc(m, 0u);     // high word = m - (m != 0)
-            od[0] = ptx::add_cc(od[0], plo);
-            od[1] = ptx::addc_cc(od[1], phi);
-        } else {
-            od[0] = ptx::mad_lo_cc(P::MOD(1), m, od[0]);
-            od[1] = ptx::madc_hi_cc(P::MOD(1), m, od[1]);
-        }
+        const uint32_t m = ev[0] * inv_word();
+        od[0] = ptx::mad_lo_cc(mod_word<1>(), m, od[0]);
+        od[1] = ptx::madc_hi_cc(mod_word<1>(), m, od[1]);
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             od[j] = ptx::madc_lo_cc(P::MOD(j + 1), m, od[j]);
             od[j + 1] = ptx::madc_hi_cc(P::MOD(j + 1), m, od[j + 1]);
         }
-        if (P::MOD(0) == 1u) {
-            ev[0] = ptx::add_cc(ev[0], m);
-            ev[1] = ptx::addc_cc(ev[1], 0u);
-        } else {
-            ev[0] = ptx::mad_lo_cc(P::MOD(0), m, ev[0]);
-            ev[1] = ptx::madc_hi_cc(P::MOD(0), m, ev[1]);
-        }
+        ev[0] = ptx::mad_lo_cc(mod_word<0>(), m, ev[0]);
+        ev[1] = ptx::madc_hi_cc(mod_word<0>(), m, ev[1]);
 #pragma unroll
         for (int j = 2; j < L; j += 2) {
             ev[j] = ptx::madc_lo_cc(P::MOD(j), m, ev[j]);

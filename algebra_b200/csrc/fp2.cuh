@@ -17,10 +17,10 @@ template <class P> struct Fp2 {
     // Base-field multiplication as a CALL on the device: an inlined Fp2 multiplication is three ~600-instruction Montgomery
     // bodies, and a G2 point addition has 14 of them — far beyond the instruction cache (the G1 kernels already show
     // `no_instruction` stalls at a third of that size) and minutes of compile time per kernel.  One shared body per kernel instead.
-#ifdef __CUDA_ARCH__
-    static __device__ __noinline__ void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
+#if defined(__CUDACC__) && !defined(AB_FP2_INLINE_MUL)
+    static __host__ __device__ __noinline__ void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
 #else
-    static inline void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
+    static AB_HD void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
 #endif
     static AB_HD void add(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::add(r, a, b); B::add(r + LB, a + LB, b + LB); }
     static AB_HD void sub(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::sub(r, a, b); B::sub(r + LB, a + LB, b + LB); }

@@ -176,6 +176,8 @@ struct EnvKnobs {
                                           // 10 groups (8 GB) 392 ms — groups shorten the batches of the later levels
     int shared_inv = 1;                   // one field inversion per block (Montgomery's trick across the block) instead of per thread
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
+    double level_min_load = 16.0;         // automatic mode: keep adding affine levels while the average bucket still holds this many entries
+    int level_cap = 4;
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
     EnvKnobs() {
@@ -185,6 +187,8 @@ struct EnvKnobs {
         if (const char *e = getenv("B200_MSM_SHARED_INV")) shared_inv = atoi(e) != 0;
         min_batch = shared_inv ? 96 : 256;   // overhead per addition: 590/(4*batch) multiplications shared, 570/batch per thread
         if (const char *e = getenv("B200_MSM_MIN_BATCH")) min_batch = std::max(8, atoi(e));
+        if (const char *e = getenv("B200_MSM_LEVEL_MIN_LOAD")) level_min_load = std::max(2.0, atof(e));
+        if (const char *e = getenv("B200_MSM_LEVEL_CAP")) level_cap = std::min(8, std::max(0, atoi(e)));
         if (const char *e = getenv("B200_MSM_FORCE_CHUNKS")) force_chunks = atoi(e);
         if (const char *e = getenv("B200_L2_FETCH_GRANULARITY")) l2_fetch_granularity = atoi(e);
     }
@@ -204,7 +208,7 @@ struct MsmTimings {
 static thread_local MsmTimings t_last;
 
 int msm_set_affine_levels(int levels) {
-    if (levels < -1 || levels > 6) { set_last_error("affine levels must be in [-1, 6]"); return B200_EINVAL; }
+    if (levels < -1 || levels > 8) { set_last_error("affine levels must be in [-1, 8]"); return B200_EINVAL; }
     t_affine_levels = levels;
     return 0;
 }
@@ -519,7 +523,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
             if (levels < 0) {
                 levels = 0;
                 if (C::AUTO_LEVELS)
-                    for (double l = (double)nk / (double)g.nb; l >= 16.0 && levels < 4; l *= 0.5) levels++;
+                    for (double l = (double)nk / (double)g.nb; l >= env_knobs().level_min_load && levels < env_knobs().level_cap; l *= 0.5) levels++;
                 // the first level must be able to give every resident thread a batch of >= 256 additions
                 if ((double)nk * g.W * 0.5 / ((double)sm_count() * 512.0) < (double)env_knobs().min_batch) levels = 0;
             }

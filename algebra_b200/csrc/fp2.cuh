@@ -14,10 +14,12 @@ template <class P> struct Fp2 {
     using B = Fp<P>;
     static constexpr int LB = P::L;
     static constexpr int L = 2 * P::L;
-    // Base-field multiplication as a CALL on the device: an inlined Fp2 multiplication is three ~600-instruction Montgomery
-    // bodies, and a G2 point addition has 14 of them — far beyond the instruction cache (the G1 kernels already show
-    // `no_instruction` stalls at a third of that size) and minutes of compile time per kernel.  One shared body per kernel instead.
-#if defined(__CUDACC__) && !defined(AB_FP2_INLINE_MUL)
+    // Base-field multiplication: inlined like everything else.  A called (__noinline__) body would cut the G2 kernels' code size and
+    // compile time by 3x, but with it msm_bucket_reduce_kernel<G2> returned wrong sums on the B200 for every bucket index >= 2 (the
+    // double-and-add of the chunk offset) while the same source passed on the host and in the element-wise kernels; the inlined
+    // build passes the whole matrix (profiles/r02_g2_debug_matrix.log: default vs variants v3 inline / v4 more calls / v5 ptxas -O1).
+    // AB_FP2_NOINLINE_MUL re-enables the call form for experiments.
+#if defined(__CUDACC__) && defined(AB_FP2_NOINLINE_MUL)
     static __host__ __device__ __noinline__ void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }
 #else
     static AB_HD void bmul(uint32_t *r, const uint32_t *a, const uint32_t *b) { B::mul(r, a, b); }

@@ -178,6 +178,7 @@ struct EnvKnobs {
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
     double level_min_load = 16.0;         // automatic mode: keep adding affine levels while the average bucket still holds this many entries
     int level_cap = 4;
+    int reduce_log_m = 6;                 // buckets per reduction thread = 2^reduce_log_m at most
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
     EnvKnobs() {
@@ -189,6 +190,7 @@ struct EnvKnobs {
         if (const char *e = getenv("B200_MSM_MIN_BATCH")) min_batch = std::max(8, atoi(e));
         if (const char *e = getenv("B200_MSM_LEVEL_MIN_LOAD")) level_min_load = std::max(2.0, atof(e));
         if (const char *e = getenv("B200_MSM_LEVEL_CAP")) level_cap = std::min(8, std::max(0, atoi(e)));
+        if (const char *e = getenv("B200_MSM_REDUCE_LOG_M")) reduce_log_m = std::min(8, std::max(0, atoi(e)));
         if (const char *e = getenv("B200_MSM_FORCE_CHUNKS")) force_chunks = atoi(e);
         if (const char *e = getenv("B200_L2_FETCH_GRANULARITY")) l2_fetch_granularity = atoi(e);
     }
@@ -221,9 +223,11 @@ int msm_set_window(int c) {
     return 0;
 }
 
-// Window choice: a time model fitted to the B200 sweeps committed in profiles/ (n = 2^26 and 2^23, BLS12-381):
-//   accumulation 0.33 ns per (point, window) with the batched-affine levels, reduction 2.6 ns per bucket,
-//   scatter + histogram 0.02 ns per entry, + contention when the top window has fewer than ~2^10 buckets.
+// Window choice: a time model fitted to the B200 sweeps of round 2 (profiles/r02_window_sweep_*.log; n = 2^22 .. 2^26, BLS12-381 G1):
+//   accumulation 0.28 ns per (point, window) when the average bucket holds >= ~100 entries (four affine levels), rising to ~0.5 ns
+//   at 32 entries per bucket (fewer levels, more XYZZ work); bucket reduction 2.1 ns per bucket; histogram + scatter 0.035 ns per
+//   entry, + contention when the top window has fewer than ~2^10 buckets; ~1.5 ms of fixed tail (reduction tree, combine).
+//   Measured optima: c = 16 for n = 2^22 .. 2^24, 17 for 2^25, 20 for 2^26 (the model is within 1-2 % of the best measured time there).
 int msm_auto_window(size_t n, int scalar_bits) {
     if (n < 32) return 3;  // same floor as the reference (:445-449)
     double best = 1e300;
@@ -231,10 +235,11 @@ int msm_auto_window(size_t n, int scalar_bits) {
     for (int c = 4; c <= 23; c++) {
         MsmGeom g = make_geom(c, scalar_bits);
         if ((double)g.total_buckets * 192.0 > 24e9) continue;
-        const double entries = (double)n * g.W;
-        double t = 0.33 * entries + 2.6 * (double)g.total_buckets + 0.02 * entries;
-        if (g.top_bits < 10) t += 0.15 * (double)n;   // hot top-window buckets serialise the atomics
-        t += 2000.0 * g.W;                             // per-window fixed costs (reduction tree, combine doublings)
+        const double entries = (double)n * g.W, load = (double)n / (double)g.nb;
+        const double per = 0.28 * (1.0 + 0.8 * std::max(0.0, (100.0 - load) / 100.0));
+        double t = per * entries + 2.1 * (double)g.total_buckets + 0.035 * entries;
+        if (g.top_bits < 10) t += 0.25 * (double)n;   // hot top-window buckets serialise the atomics
+        t += 1.5e6 + 25e3 * g.W;                       // fixed tail + per-window costs
         if (t < best) { best = t; best_c = c; }
     }
     return best_c;
@@ -565,7 +570,10 @@ template <class C> struct MsmSession final : MsmSessionBase {
         if (chunks_done == 0) AB_CUDA(cudaMemsetAsync(buckets, 0, nb_total * 4 * L * 4, st));
         AB_CUDA(cudaEventRecord(e_acc_done, st));
         // reduction geometry: chunk of m = 2^log_m buckets per thread
-        int log_m = 5;
+        // (each thread pays ~300 multiplications for its chunk-offset product on top of 28 per bucket: longer chunks amortise it, as long as
+        // W * nb / m threads still fill the machine a few times over)
+        int log_m = env_knobs().reduce_log_m;
+        while (log_m > 5 && ((size_t)g.W * g.nb >> log_m) < (size_t)sm_count() * 512) log_m--;
         while (log_m > 0 && (g.nb >> log_m) < 64) log_m--;
         const uint32_t max_nb = std::max(g.nb, g.nb_top);
         const uint32_t chunks = (max_nb + (1u << log_m) - 1) >> log_m;

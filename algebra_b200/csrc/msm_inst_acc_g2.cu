@@ -1,5 +1,7 @@
-// explicit instantiation: MsmAccLaunch<CurveBlsG2> (see msm_common.cuh)
+// explicit instantiation: MsmAccLaunch<CurveBlsG2>::accumulate / occupancy (digits and merge: msm_inst_acc2_g2.cu)
 #include "msm_k_acc.cuh"
 namespace ab200 {
-template struct MsmAccLaunch<CurveBlsG2>;
+template int MsmAccLaunch<CurveBlsG2>::occupancy(bool);
+template int MsmAccLaunch<CurveBlsG2>::accumulate(bool, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t *, uint32_t *,
+                                                  uint32_t *, uint32_t *, uint32_t *, cudaStream_t);
 }  // namespace ab200

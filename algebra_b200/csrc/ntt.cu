@@ -47,7 +47,7 @@ struct NttPassParams {
 };
 
 // shared-memory tile: two 16-byte planes so that consecutive elements are consecutive uint4 (conflict-free)
-template <class P>
+template <class P, bool FUSE_LAST2>
 __global__ void __launch_bounds__(512, 2) ntt_pass_kernel(const uint4 *in, uint4 *out, NttPassParams pp) {
     using F = Fp<P>;
     extern __shared__ uint4 smem[];
@@ -96,10 +96,14 @@ __global__ void __launch_bounds__(512, 2) ntt_pass_kernel(const uint4 *in, uint4
     __syncthreads();
 
     // ---- r DIF stages: lo' = lo + hi ; hi' = (lo - hi) * w     (butterfly_fn_io, fft.rs:190-198)
+    // The last two stages (gaps 2 and 1) are fused into one radix-4 step on 4 consecutive rows held in registers: three of its four
+    // butterflies have w = 1, so it costs ONE twiddle multiplication (by the 4th root of unity) per 4 elements instead of two, and
+    // saves a barrier and a shared-memory round trip.
     {
         const bool active = tid < tile / 2;
         const int g = tid & (G - 1), u = tid >> logG;
-        for (int s = 0; s < r; s++) {
+        const int radix2_stages = (FUSE_LAST2 && r >= 2) ? r - 2 : r;
+        for (int s = 0; s < radix2_stages; s++) {
             if (active) {
                 const int gaplog = r - 1 - s;
                 const int j = u & ((1 << gaplog) - 1);
@@ -122,6 +126,32 @@ __global__ void __launch_bounds__(512, 2) ntt_pass_kernel(const uint4 *in, uint4
                 s_hi[li] = make_uint4(x[4], x[5], x[6], x[7]);
                 s_lo[hi] = make_uint4(d[0], d[1], d[2], d[3]);
                 s_hi[hi] = make_uint4(d[4], d[5], d[6], d[7]);
+            }
+            __syncthreads();
+        }
+        if (FUSE_LAST2 && r >= 2) {
+            if (tid < tile / 4) {   // group (q, g): rows 4q .. 4q+3 of column g
+                const int q = tid >> logG, base = ((4 * q) << logG) + g;
+                uint32_t x[4][8], t[8], w[8];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint4 a = s_lo[base + (e << logG)], b = s_hi[base + (e << logG)];
+                    x[e][0] = a.x; x[e][1] = a.y; x[e][2] = a.z; x[e][3] = a.w; x[e][4] = b.x; x[e][5] = b.y; x[e][6] = b.z; x[e][7] = b.w;
+                }
+                F::sub(t, x[0], x[2]); F::add(x[0], x[0], x[2]); limbs_copy<8>(x[2], t);          // gap 2, j = 0: w = 1
+                F::sub(t, x[1], x[3]); F::add(x[1], x[1], x[3]);                                  // gap 2, j = 1: w = w_4 = w_256^64
+                {
+                    const uint4 w0 = __ldg(pp.tw_small + 2 * 64), w1 = __ldg(pp.tw_small + 2 * 64 + 1);
+                    w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+                }
+                F::mul(x[3], t, w);
+                F::sub(t, x[0], x[1]); F::add(x[0], x[0], x[1]); limbs_copy<8>(x[1], t);          // gap 1
+                F::sub(t, x[2], x[3]); F::add(x[2], x[2], x[3]); limbs_copy<8>(x[3], t);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    s_lo[base + (e << logG)] = make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]);
+                    s_hi[base + (e << logG)] = make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]);
+                }
             }
             __syncthreads();
         }
@@ -560,10 +590,13 @@ static EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 struct NttKnobs {
-    int logG = 1, generation = 2;
+    int logG = 1, generation = 1, fuse_last2 = 1;
     NttKnobs() {
         if (const char *e = getenv("B200_NTT_LOGG")) logG = std::min(3, std::max(0, atoi(e)));   // first-generation kernel: columns per block
-        if (const char *e = getenv("B200_NTT_GENERATION")) generation = atoi(e) == 1 ? 1 : 2;
+        // generation 1 (block tiles, LDG/STS) is the default: 3.86 ms vs 4.02 ms for generation 2 (TMA-staged warp tiles) @2^24 on the
+        // B200 (profiles/r02_ntt_gen1_vs_gen2_fused.jsonl) — the kernel is bound by the integer pipe, not by tile movement
+        if (const char *e = getenv("B200_NTT_GENERATION")) generation = atoi(e) == 2 ? 2 : 1;
+        if (const char *e = getenv("B200_NTT_FUSE_LAST2")) fuse_last2 = atoi(e) != 0;
     }
 };
 static const NttKnobs &ntt_knobs() {
@@ -705,7 +738,8 @@ template <class P> static int ntt_run(int field, uint4 *d_data, int log_n, bool 
         const unsigned blocks = (unsigned)(n >> (pp.r + logG));
         const uint4 *src = (t == 0) ? d_data : scratch;
         uint4 *dst = pp.is_last ? d_data : scratch;
-        ntt_pass_kernel<P><<<blocks, threads, (size_t)tile * 32, st>>>(src, dst, pp);
+        if (ntt_knobs().fuse_last2) ntt_pass_kernel<P, true><<<blocks, threads, (size_t)tile * 32, st>>>(src, dst, pp);
+        else ntt_pass_kernel<P, false><<<blocks, threads, (size_t)tile * 32, st>>>(src, dst, pp);
         AB_LAUNCHED();
         log_seg = logB;
     }

@@ -31,6 +31,13 @@ struct Bn254G1 {
     static constexpr int FIELD_ID = B200_FIELD_BN254_FR;
 };
 
+// G2 of BLS12-381: coordinates in Fq2 = (c0, c1), 12 u64 per coordinate (curves/bls12_381/src/curves/g2.rs:54)
+struct Bls12_381G2 {
+    static constexpr int ID = B200_CURVE_BLS12_381_G2, N = 12;
+    using ScalarParams = BlsFr;
+    static constexpr int FIELD_ID = B200_FIELD_BLS12_381_FR;
+};
+
 struct B200Error : std::runtime_error {
     int code;
     B200Error(int c) : std::runtime_error(std::string("algebra_b200: ") + b200_last_error()), code(c) {}
@@ -59,10 +66,55 @@ template <class Curve> struct VariableBaseMSM {
         if (bases.size() != scalars.size()) return bases.size() < scalars.size() ? bases.size() : scalars.size();
         return msm_unchecked(bases, scalars);
     }
+    // the same hook on `ngpus` devices of the node, driven from this one process (b200_msm_sw_g1_multi); ngpus = 0: all of them
+    static Projective<Curve> msm_unchecked_multi(const std::vector<Affine<Curve>> &bases, const std::vector<Fr> &scalars, int ngpus = 0) {
+        const size_t n = bases.size() < scalars.size() ? bases.size() : scalars.size();
+        Projective<Curve> out{};
+        check(b200_msm_sw_g1_multi(Curve::ID, ngpus > 0 ? ngpus : b200_device_count(), reinterpret_cast<const uint64_t *>(bases.data()),
+                                   reinterpret_cast<const uint64_t *>(scalars.data()), n, reinterpret_cast<uint64_t *>(&out)));
+        return out;
+    }
+    // VariableBaseMSM::msm_chunks (variable_base/mod.rs:119-150) on the streaming entry points: `step` pairs per push, one reduction
+    static Projective<Curve> msm_chunks(const std::vector<Affine<Curve>> &bases, const std::vector<Fr> &scalars, size_t step) {
+        if (scalars.size() > bases.size()) throw std::invalid_argument("scalars_stream.len() <= bases_stream.len()");
+        const size_t ns = scalars.size(), skip = bases.size() - ns;   // `skip(bases.len() - scalars.len())`
+        Projective<Curve> out{};
+        if (ns == 0) return msm_unchecked({}, {});
+        if (step == 0) step = ns;
+        b200_msm_stream_t *st = nullptr;
+        check(b200_msm_stream_begin(Curve::ID, B200_SCALARS_FR_MONT, ns, step < ns ? step : ns, &st));
+        for (size_t lo = 0; lo < ns; lo += step) {
+            const size_t cnt = lo + step <= ns ? step : ns - lo;
+            const int rc = b200_msm_stream_push(st, reinterpret_cast<const uint64_t *>(bases.data() + skip + lo), scalars.data() + lo, cnt);
+            if (rc) { b200_msm_stream_abort(st); throw B200Error(rc); }
+        }
+        check(b200_msm_stream_finish(st, reinterpret_cast<uint64_t *>(&out)));
+        return out;
+    }
     static Affine<Curve> into_affine(const Projective<Curve> &p) {
         Affine<Curve> a{};
         check(b200_g1_into_affine(Curve::ID, reinterpret_cast<const uint64_t *>(&p), reinterpret_cast<uint64_t *>(&a)));
         return a;
+    }
+};
+
+// Bases kept in HBM across MSM calls (an SRS), sharded over `ngpus` devices: b200_bases_upload / b200_msm_bases / b200_bases_free
+template <class Curve> class ResidentBases {
+    b200_bases_t *h_ = nullptr;
+    size_t n_ = 0;
+
+  public:
+    explicit ResidentBases(const std::vector<Affine<Curve>> &bases, int ngpus = 0) : n_(bases.size()) {
+        check(b200_bases_upload(Curve::ID, ngpus > 0 ? ngpus : b200_device_count(), reinterpret_cast<const uint64_t *>(bases.data()), bases.size(), &h_));
+    }
+    ResidentBases(const ResidentBases &) = delete;
+    ResidentBases &operator=(const ResidentBases &) = delete;
+    ~ResidentBases() { b200_bases_free(h_); }
+    MsmResult<Curve> msm(const std::vector<Fr> &scalars) const {
+        if (scalars.size() != n_) return scalars.size() < n_ ? scalars.size() : n_;
+        Projective<Curve> out{};
+        check(b200_msm_bases(h_, B200_SCALARS_FR_MONT, scalars.data(), scalars.size(), reinterpret_cast<uint64_t *>(&out)));
+        return out;
     }
 };
 

@@ -24,6 +24,40 @@ int main(int argc, char **argv) {
         scalars.resize(3);
         auto p = std::get<0>(VariableBaseMSM<Bls12_381G1>::msm(bases, scalars));   // identity bases -> identity
         printf("gpu_msm_identity %d\n", (int)(p.z == Fq<Bls12_381G1>{}));
+        // every MSM entry point through the header only, on all devices of the box: bases {G x 5000}, scalars i -> (sum i) * G
+        {
+            using C = Bls12_381G1;
+            Affine<C> G{};
+            for (int i = 0; i < 6; i++) {
+                G.x[i] = (uint64_t)BlsFq::GEN_X(2 * i) | ((uint64_t)BlsFq::GEN_X(2 * i + 1) << 32);
+                G.y[i] = (uint64_t)BlsFq::GEN_Y(2 * i) | ((uint64_t)BlsFq::GEN_Y(2 * i + 1) << 32);
+            }
+            auto fr_of = [](uint64_t k) {
+                uint32_t l[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
+                Fp<BlsFr>::to_mont(l, l);
+                Fr r;
+                for (int i = 0; i < 4; i++) r[i] = (uint64_t)l[2 * i] | ((uint64_t)l[2 * i + 1] << 32);
+                return r;
+            };
+            const size_t n = 5000;
+            std::vector<Affine<C>> B(n, G);
+            std::vector<Fr> S(n);
+            uint64_t total = 0;
+            for (size_t i = 0; i < n; i++) { S[i] = fr_of(i + 1); total += i + 1; }
+            auto aff = [](const Projective<C> &p) { return VariableBaseMSM<C>::into_affine(p); };
+            auto same = [](const Affine<C> &a, const Affine<C> &b) { return a.x == b.x && a.y == b.y; };
+            const Affine<C> want = aff(VariableBaseMSM<C>::msm_unchecked({G}, {fr_of(total)}));
+            const int devices = b200_device_count();
+            printf("gpu_devices %d\n", devices);
+            printf("gpu_msm_single %d\n", (int)same(aff(VariableBaseMSM<C>::msm_unchecked(B, S)), want));
+            printf("gpu_msm_multi %d\n", (int)same(aff(VariableBaseMSM<C>::msm_unchecked_multi(B, S, devices)), want));
+            printf("gpu_msm_chunks %d\n", (int)same(aff(VariableBaseMSM<C>::msm_chunks(B, S, 1200)), want));
+            ResidentBases<C> srs(B, devices);
+            printf("gpu_msm_resident %d\n", (int)same(aff(std::get<0>(srs.msm(S))), want));
+            S.pop_back();
+            auto r2 = srs.msm(S);
+            printf("gpu_resident_mismatch %d\n", (int)(std::holds_alternative<size_t>(r2) && std::get<size_t>(r2) == n - 1));
+        }
         std::vector<Fr> v(8, d.size_inv);
         auto dom8 = Radix2EvaluationDomain<Bls12_381G1>::make(8).value();
         auto w = dom8.ifft(dom8.fft(v));

@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/g_gpus.txt
-timeout 900 python -m pytest tests/test_gpu_dist_nccl.py -q > gpurun_out/g_pytest_dist.log 2>&1; echo "rc=$?" >> gpurun_out/g_pytest_dist.log; tail -4 gpurun_out/g_pytest_dist.log
+timeout 900 python -m pytest tests/test_gpu_dist_nccl.py tests/test_cpp_mirror.py -q > gpurun_out/g_pytest_dist.log 2>&1; echo "rc=$?" >> gpurun_out/g_pytest_dist.log; tail -4 gpurun_out/g_pytest_dist.log
 P=29500
 for n in 8 4 2; do
   P=$((P+1))

@@ -178,6 +178,7 @@ struct EnvKnobs {
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
     double level_min_load = 16.0;         // automatic mode: keep adding affine levels while the average bucket still holds this many entries
     int level_cap = 4;
+    int stagger = 0;                      // generation-2 pair-add: unequal batches inside groups of four blocks (desynchronises the inversions)
     int reduce_log_m = 6;                 // buckets per reduction thread = 2^reduce_log_m at most
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
@@ -190,6 +191,7 @@ struct EnvKnobs {
         if (const char *e = getenv("B200_MSM_MIN_BATCH")) min_batch = std::max(8, atoi(e));
         if (const char *e = getenv("B200_MSM_LEVEL_MIN_LOAD")) level_min_load = std::max(2.0, atof(e));
         if (const char *e = getenv("B200_MSM_LEVEL_CAP")) level_cap = std::min(8, std::max(0, atoi(e)));
+        if (const char *e = getenv("B200_MSM_STAGGER")) stagger = atoi(e) != 0;
         if (const char *e = getenv("B200_MSM_REDUCE_LOG_M")) reduce_log_m = std::min(8, std::max(0, atoi(e)));
         if (const char *e = getenv("B200_MSM_FORCE_CHUNKS")) force_chunks = atoi(e);
         if (const char *e = getenv("B200_L2_FETCH_GRANULARITY")) l2_fetch_granularity = atoi(e);
@@ -468,7 +470,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 msm_pairmap_kernel<<<(unsigned)((out_cap + 1023) / 1024), 256, 0, st>>>(cur_offsets, off2, (uint32_t)nbg, pairmap);
                 AB_LAUNCHED();
             }
-            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts, env_knobs().shared_inv, st)) return rc;
+            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts, env_knobs().shared_inv, (variant == 2 && env_knobs().shared_inv) ? env_knobs().stagger : 0, st)) return rc;
             arena.release(pairmap);
             // the level before the previous one is no longer read
             arena.release(lvl_pts[lv & 1]);

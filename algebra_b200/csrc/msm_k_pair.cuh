@@ -1,5 +1,6 @@
 // msm_k_pair.cuh — batched-affine pair-add kernels (both generations) and their launcher.
 #pragma once
+#include <algorithm>
 #include "msm_common.cuh"
 
 namespace ab200 {
@@ -271,14 +272,25 @@ template <int L> __device__ __forceinline__ void strip_read(uint32_t *r, const u
 template <class C, bool FIRST, int MINB>
 __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
                                                                 const uint32_t *__restrict__ pairmap, const uint32_t *__restrict__ offsets_out,
-                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out, int shared_inv) {
+                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out, int shared_inv, int stagger) {
     using F = typename C::F;
     constexpr int L = F::L;
+    uint64_t stagger_base = 0;
     extern __shared__ uint4 strip[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(strip);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t M = __ldg(offsets_out + nb);
-    const uint64_t w_lo = (uint64_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * 32 * batch;
+    // Staggered batches: the four blocks of a group (blockIdx & 3) get batches of 100 / 85 / 70 / 55 % of `batch`, so that blocks
+    // resident on one SM drift out of phase — otherwise every block of a wave reaches its (single-warp) block inversion at the same
+    // time and the SM runs on a quarter of its warps for ~10 % of the kernel (ncu: 1.1 warps per issue stalled on the barrier).
+    if (stagger) {
+        const uint32_t r4 = blockIdx.x & 3, b0 = batch, b1 = max(8u, batch * 17 / 20), b2 = max(8u, batch * 14 / 20), b3 = max(8u, batch * 11 / 20);
+        const uint32_t mine = r4 == 0 ? b0 : r4 == 1 ? b1 : r4 == 2 ? b2 : b3;
+        const uint32_t before = r4 == 0 ? 0 : r4 == 1 ? b0 : r4 == 2 ? b0 + b1 : b0 + b1 + b2;
+        stagger_base = ((uint64_t)(blockIdx.x >> 2) * (b0 + b1 + b2 + b3) + before) * 128;
+        batch = mine;
+    }
+    const uint64_t w_lo = (stagger ? stagger_base : (uint64_t)blockIdx.x * 128 * batch) + (uint64_t)(threadIdx.x >> 5) * 32 * batch;
     const bool active = w_lo + lane < M;
     if (!active && !shared_inv) return;   // (with the block-shared inversion every thread has to reach the barriers)
     const uint32_t w_hi = (uint32_t)min((uint64_t)M, w_lo + (uint64_t)32 * batch);
@@ -425,18 +437,24 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
 
 template <class C>
 int MsmPairLaunch<C>::run(int variant, bool first, const uint32_t *bases, const uint32_t *src, const uint32_t *offsets_in, const uint32_t *offsets_out,
-                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, cudaStream_t st) {
+                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, int stagger, cudaStream_t st) {
     constexpr int L = C::F::L;
     if (variant == 2) {
-        const size_t warps = (out_cap + (size_t)32 * batch - 1) / ((size_t)32 * batch);
-        const unsigned pg = (unsigned)((warps + 3) / 4);
+        unsigned pg;
+        if (stagger) {   // groups of four blocks with batches b, 0.85 b, 0.7 b, 0.55 b (see the kernel)
+            const size_t S = (size_t)batch + std::max(8u, batch * 17 / 20) + std::max(8u, batch * 14 / 20) + std::max(8u, batch * 11 / 20);
+            pg = (unsigned)(4 * ((out_cap + 128 * S - 1) / (128 * S)));
+        } else {
+            const size_t warps = (out_cap + (size_t)32 * batch - 1) / ((size_t)32 * batch);
+            pg = (unsigned)((warps + 3) / 4);
+        }
         const size_t smem = (size_t)5 * (L / 4) * 128 * 16;
         if (first) {
             AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, true, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv);
+            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger);
         } else {
             AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, false, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv);
+            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger);
         }
     } else {
         const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);

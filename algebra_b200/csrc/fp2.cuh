@@ -52,6 +52,7 @@ template <class P> struct Fp2 {
     }
     static AB_HD void set_one(uint32_t *r) { B::set_one(r); B::set_zero(r + LB); }
     static AB_HD void set_zero(uint32_t *r) { B::set_zero(r); B::set_zero(r + LB); }
+    static AB_HD void inv_lowlat(uint32_t *r, const uint32_t *a) { inv(r, a); }
     static AB_HD void inv(uint32_t *r, const uint32_t *a) {
         uint32_t n[LB], t[LB];
         bmul(n, a, a);

@@ -177,7 +177,7 @@ struct EnvKnobs {
     int shared_inv = 1;                   // one field inversion per block (Montgomery's trick across the block) instead of per thread
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
     double level_min_load = 16.0;         // automatic mode: keep adding affine levels while the average bucket still holds this many entries
-    int level_cap = 4;
+    int level_cap = 8;                    // upper bound on top of the per-curve LEVEL_CAP
     int stagger = 0;                      // generation-2 pair-add: unequal batches inside groups of four blocks (desynchronises the inversions)
     int reduce_log_m = 6;                 // buckets per reduction thread = 2^reduce_log_m at most
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
@@ -530,9 +530,9 @@ template <class C> struct MsmSession final : MsmSessionBase {
             if (levels < 0) {
                 levels = 0;
                 if (C::AUTO_LEVELS)
-                    for (double l = (double)nk / (double)g.nb; l >= env_knobs().level_min_load && levels < env_knobs().level_cap; l *= 0.5) levels++;
+                    for (double l = (double)nk / (double)g.nb; l >= env_knobs().level_min_load && levels < std::min(env_knobs().level_cap, C::LEVEL_CAP); l *= 0.5) levels++;
                 // the first level must be able to give every resident thread a batch of >= 256 additions
-                if ((double)nk * g.W * 0.5 / ((double)sm_count() * 512.0) < (double)env_knobs().min_batch) levels = 0;
+                if ((double)nk * g.W * 0.5 / ((double)sm_count() * C::PAIR_MINB * 128.0) < (double)env_knobs().min_batch) levels = 0;
             }
             if (levels == 0) {
                 if (int rc = accumulate(bas, sorted, offsets, nb_total, nk * (size_t)g.W, target)) return rc;
@@ -545,7 +545,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min(budget, 0.6 * (double)free_b + pool_reserved_bytes());
                 int gw = (int)std::floor(budget / per_window);
                 // ... and a group must give every resident thread a batch of >= min_batch additions at level 1
-                const int gw_min = (int)std::ceil((double)env_knobs().min_batch * (double)sm_count() * 512.0 / ((double)nk * 0.5));
+                const int gw_min = (int)std::ceil((double)env_knobs().min_batch * (double)sm_count() * C::PAIR_MINB * 128.0 / ((double)nk * 0.5));
                 gw = std::max(std::max(1, gw_min), std::min(g.W, gw));
                 gw = std::min(g.W, gw);
                 const int ngroups = (g.W + gw - 1) / gw;

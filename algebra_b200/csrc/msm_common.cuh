@@ -16,15 +16,18 @@ struct CurveBls {
     using Fr = BlsFr;
     static constexpr int SCALAR_BITS = 255;  // Fr::MODULUS_BIT_SIZE (variable_base/mod.rs:451)
     static constexpr bool AUTO_LEVELS = true;
+    static constexpr int LEVEL_CAP = 4;      // automatic mode: at most this many batched-affine levels
     static constexpr int PAIR_MINB = 4;      // resident blocks per SM the pair-add kernels are compiled for (128 registers)
 };
 struct CurveBn {
     using F = Fp<BnFq>;
     using Fr = BnFr;
     static constexpr int SCALAR_BITS = 254;
-    // 8-limb coordinates: the affine additions are 2.2x cheaper in multiplies but move almost as many bytes, and the levels
-    // measured slower (BN254 2^24: 49 -> 55 ms), so the automatic mode keeps them for the 12-limb field only
-    static constexpr bool AUTO_LEVELS = false;
+    // 8-limb coordinates: the affine additions are 2.2x cheaper in multiplies but move almost as many bytes.  With the generation-1
+    // kernel the levels measured slower (BN254 2^24: 49 -> 55 ms, round 1); with generation 2 they win: 49.4 ms without, 45.1 ms with
+    // 3 levels, 45.9 ms with 4 (profiles/r02_levels_bn254_g2.log)
+    static constexpr bool AUTO_LEVELS = true;
+    static constexpr int LEVEL_CAP = 3;
     static constexpr int PAIR_MINB = 4;
 };
 // G2 of BLS12-381: coordinates in Fq2 (curves/bls12_381/src/curves/g2.rs:54), same scalar field
@@ -32,7 +35,8 @@ struct CurveBlsG2 {
     using F = Fp2<BlsFq>;
     using Fr = BlsFr;
     static constexpr int SCALAR_BITS = 255;
-    static constexpr bool AUTO_LEVELS = false;
+    static constexpr bool AUTO_LEVELS = true;   // G2 2^22: 100.4 ms without levels, 80.4 ms with 3, 74.4 ms with 4 (profiles/r02_levels_bn254_g2.log)
+    static constexpr int LEVEL_CAP = 4;
     static constexpr int PAIR_MINB = 2;      // 24-word coordinates: 255 registers, two blocks per SM
 };
 

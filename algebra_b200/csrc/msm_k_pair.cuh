@@ -53,6 +53,10 @@ template <class F> __device__ __forceinline__ int pair_classify(uint32_t *den, c
 // peels the 128 inverses back out; every thread then picks up 1/run of its own product.  A per-thread inversion costs ~570
 // multiplications of issue time PER WARP; this costs ~590 per BLOCK, i.e. a quarter — which is what allows short batches.
 // `sm` holds 128 * L words (word i of thread t at sm[i * 128 + t]); all 128 threads of the block must call this.
+#ifndef AB_BLOCK_INVERSE_LOWLAT
+#define AB_BLOCK_INVERSE_LOWLAT 1
+#endif
+static constexpr bool kBlockInverseLowLatency = AB_BLOCK_INVERSE_LOWLAT != 0;
 template <class F> __device__ __forceinline__ void shfl_limbs(uint32_t *r, const uint32_t *a, int src_lane) {
 #pragma unroll
     for (int i = 0; i < F::L; i++) r[i] = __shfl_sync(0xffffffffu, a[i], src_lane);
@@ -88,7 +92,8 @@ template <class F> __device__ __noinline__ void block_inverse(uint32_t *inv, con
         }
         uint32_t I[L];
         shfl_limbs<F>(y, P, 31);
-        F::inv(I, y);                                 // 1 / (product of all 128), computed redundantly by the 32 lanes
+        if (kBlockInverseLowLatency) F::inv_lowlat(I, y);   // 1 / (product of all 128), computed redundantly by the 32 lanes
+        else F::inv(I, y);
         shfl_limbs<F>(y, P, lane ? lane - 1 : 0);
         if (lane) F::mul(I, I, y);                    // ... times the products of the other lanes = 1 / a3
         shfl_limbs<F>(y, S, lane < 31 ? lane + 1 : 31);

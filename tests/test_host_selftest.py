@@ -53,6 +53,10 @@ def test_fp_ops(lib, fid, f):
         out = np.empty_like(A)
         assert lib.selftest_fp_op({0: 4, 2: 5}[fid], 0, _p(A.view(np.uint32)), _p(B.view(np.uint32)), _p(out.view(np.uint32)), len(a)) == 0
         assert (out == C.fp_op(fid, "mul", A, B)).all()
+    nz = np.ascontiguousarray(A[1:40])   # windowed / symmetric-squaring inversion (block-shared inversion of the MSM) == a^(p-2)
+    out = np.empty_like(nz)
+    assert lib.selftest_fp_op(fid, 10, _p(nz.view(np.uint32)), _p(nz.view(np.uint32)), _p(out.view(np.uint32)), len(nz)) == 0
+    assert (out == C.fp_op(fid, "inv", nz)).all()
     canon = np.ascontiguousarray(C.fp_op(fid, "into_bigint", A))
     out = np.empty_like(A)
     lib.selftest_fp_op(fid, 7, _p(canon.view(np.uint32)), _p(canon.view(np.uint32)), _p(out.view(np.uint32)), len(a))

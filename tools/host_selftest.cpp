@@ -22,6 +22,7 @@ template <class P> static int fp_op(int op, const uint32_t *a, const uint32_t *b
             case 7: F::to_mont(r, x); break;
             case 8: F::inv(r, x); break;
             case 9: F::sqr_sos(r, x); break;
+            case 10: F::inv_lowlat(r, x); break;
             default: return 2;
         }
     }

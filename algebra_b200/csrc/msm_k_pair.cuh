@@ -53,8 +53,11 @@ template <class F> __device__ __forceinline__ int pair_classify(uint32_t *den, c
 // peels the 128 inverses back out; every thread then picks up 1/run of its own product.  A per-thread inversion costs ~570
 // multiplications of issue time PER WARP; this costs ~590 per BLOCK, i.e. a quarter — which is what allows short batches.
 // `sm` holds 128 * L words (word i of thread t at sm[i * 128 + t]); all 128 threads of the block must call this.
+// Fp::inv_lowlat (4-bit windows + symmetric squaring) in the block inversion measured SLOWER on the B200: 2^23 MSM 47.2 -> 53.6 ms,
+// 2^24 85.2 -> 92.4 ms, 2^26 unchanged (profiles/r02_bench_lowlat_inversion.log) — the table lives in local memory and sqr_sos has
+// more carry-ripple adds than mul(a, a); the plain square-and-multiply stays.
 #ifndef AB_BLOCK_INVERSE_LOWLAT
-#define AB_BLOCK_INVERSE_LOWLAT 1
+#define AB_BLOCK_INVERSE_LOWLAT 0
 #endif
 static constexpr bool kBlockInverseLowLatency = AB_BLOCK_INVERSE_LOWLAT != 0;
 template <class F> __device__ __forceinline__ void shfl_limbs(uint32_t *r, const uint32_t *a, int src_lane) {

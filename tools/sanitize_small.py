@@ -13,7 +13,7 @@ from algebra_b200 import variable_base as VB
 
 L = _lib.lib()
 st = torch.cuda.current_stream().cuda_stream
-for cid, N in ((0, 6), (1, 4)):
+for cid, N in ((0, 6), (1, 4), (2, 12)):
     n = 1 << 11
     d_bases = torch.empty((n, 2 * N), dtype=torch.int64, device="cuda")
     d_b = torch.empty((n,), dtype=torch.int64, device="cuda")
@@ -26,7 +26,21 @@ for cid, N in ((0, 6), (1, 4)):
         a = ab.into_affine(cid, ab.msm(cid, d_bases, d_s))
         ref = a if ref is None else ref
         assert (a == ref).all()
+    # batched-affine levels forced on at this small size: pairmap + generation-2 pair-add (cp.async strips, block-shared inversion
+    # through shared memory and barriers) and, with B200_MSM_PAIR_VARIANT=1, the generation-1 kernel
+    for levels, c in ((1, 5), (2, 6), (3, 4)):
+        VB.set_affine_levels(levels)
+        VB.set_window(c)
+        assert (ab.into_affine(cid, ab.msm(cid, d_bases, d_s)) == ref).all()
+    VB.set_affine_levels(-1)
     VB.set_window(0)
+    stream = VB.MsmStream(cid, 700, n)                            # streaming entry points (two staging buffers, merge kernel)
+    hb, hs = d_bases.cpu().numpy().view(np.uint64), d_s.cpu().numpy().view(np.uint64)
+    for lo in range(0, n, 700):
+        stream.push(hb[lo:lo + 700], hs[lo:lo + 700])
+    assert (ab.into_affine(cid, stream.finish()) == ref).all()
+    if cid == 2:
+        continue                                                  # the remaining calls are G1 / scalar-field only
     same = torch.zeros_like(d_s)
     same[:] = d_s[0]
     ab.msm(cid, d_bases, same)                                   # heavy buckets: head/tail partials + both fix-up kernels
@@ -46,4 +60,11 @@ for cid, N in ((0, 6), (1, 4)):
     co.ifft_in_place(x)
     assert torch.equal(x, x0)
     ab.poly_mul(cid, x[:300], x[300:500])
+    dom16 = ab.Radix2EvaluationDomain.new(cid, 1 << 16)            # >= 2^16: the TMA kernel when B200_NTT_GENERATION=2
+    y = torch.empty((1 << 16, 4), dtype=torch.int64, device="cuda")
+    _lib.check(L.b200_gen_scalars_dev(cid, 10, 1 << 16, y.data_ptr(), st))
+    y0 = y.clone()
+    dom16.fft_in_place(y)
+    dom16.ifft_in_place(y)
+    assert torch.equal(y, y0)
 print("sanitize workload ok; launches:", L.b200_launch_count())

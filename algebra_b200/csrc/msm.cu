@@ -180,6 +180,7 @@ struct EnvKnobs {
     int level_cap = 8;                    // upper bound on top of the per-curve LEVEL_CAP
     int stagger = 0;                      // generation-2 pair-add: unequal batches inside groups of four blocks (desynchronises the inversions)
     int reduce_log_m = 6;                 // buckets per reduction thread = 2^reduce_log_m at most
+    bool reduce_log_m_forced = false;     // set through the environment: used as given (tuning runs)
     int force_chunks = 0;                 // test hook: split device-resident inputs into this many chunks
     int l2_fetch_granularity = 0;         // cudaLimitMaxL2FetchGranularity during the MSM (0 = leave alone)
     EnvKnobs() {
@@ -192,7 +193,7 @@ struct EnvKnobs {
         if (const char *e = getenv("B200_MSM_LEVEL_MIN_LOAD")) level_min_load = std::max(2.0, atof(e));
         if (const char *e = getenv("B200_MSM_LEVEL_CAP")) level_cap = std::min(8, std::max(0, atoi(e)));
         if (const char *e = getenv("B200_MSM_STAGGER")) stagger = atoi(e) != 0;
-        if (const char *e = getenv("B200_MSM_REDUCE_LOG_M")) reduce_log_m = std::min(8, std::max(0, atoi(e)));
+        if (const char *e = getenv("B200_MSM_REDUCE_LOG_M")) { reduce_log_m = std::min(8, std::max(0, atoi(e))); reduce_log_m_forced = true; }
         if (const char *e = getenv("B200_MSM_FORCE_CHUNKS")) force_chunks = atoi(e);
         if (const char *e = getenv("B200_L2_FETCH_GRANULARITY")) l2_fetch_granularity = atoi(e);
     }
@@ -575,7 +576,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
         // (each thread pays ~300 multiplications for its chunk-offset product on top of 28 per bucket: longer chunks amortise it, as long as
         // W * nb / m threads still fill the machine a few times over)
         int log_m = env_knobs().reduce_log_m;
-        while (log_m > 5 && ((size_t)g.W * g.nb >> log_m) < (size_t)sm_count() * 512) log_m--;
+        while (!env_knobs().reduce_log_m_forced && log_m > 5 && ((size_t)g.W * g.nb >> log_m) < (size_t)sm_count() * 512) log_m--;
         while (log_m > 0 && (g.nb >> log_m) < 64) log_m--;
         const uint32_t max_nb = std::max(g.nb, g.nb_top);
         const uint32_t chunks = (max_nb + (1u << log_m) - 1) >> log_m;

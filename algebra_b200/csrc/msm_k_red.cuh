@@ -120,6 +120,7 @@ template <class F> struct CoopSlots {
     __device__ __forceinline__ void mul(int n, int d0, int a0, int b0, int d1 = 0, int a1 = 0, int b1 = 0, int d2 = 0, int a2 = 0, int b2 = 0, int d3 = 0,
                                         int a3 = 0, int b3 = 0) const {
         const int lane = threadIdx.x & 31;
+        __syncwarp();   // every lane has finished reading the slots (uniform branch conditions) before any of them is overwritten
         if (lane < n) {
             const int d = lane == 0 ? d0 : lane == 1 ? d1 : lane == 2 ? d2 : d3;
             const int a = lane == 0 ? a0 : lane == 1 ? a1 : lane == 2 ? a2 : a3;
@@ -144,7 +145,9 @@ template <class C> __global__ void __launch_bounds__(32) msm_window_combine_coop
     __shared__ uint32_t sm[NSLOT * L];
     CoopSlots<F> S{sm};
     const int lane = threadIdx.x;
-    auto lane0 = [&](auto fn) { if (lane == 0) fn(); __syncwarp(); };
+    // (the leading __syncwarp keeps lane 0 from overwriting a slot that another lane is still reading for a warp-uniform test:
+    // lanes of a warp are not guaranteed to run in lockstep — compute-sanitizer racecheck flagged exactly that)
+    auto lane0 = [&](auto fn) { __syncwarp(); if (lane == 0) fn(); __syncwarp(); };
     lane0([&] { F::set_one(S.at(X)); F::set_one(S.at(Y)); F::set_zero(S.at(Z)); });
     for (int w = W - 1; w >= 0; w--) {
         // ---- operand: XYZZ window sum -> Jacobian (x*zz, y*zzz, zz)  (From<Bucket> for Projective, bucket.rs:389-398)

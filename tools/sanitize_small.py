@@ -19,7 +19,7 @@ for cid, N in ((0, 6), (1, 4), (2, 12)):
     d_b = torch.empty((n,), dtype=torch.int64, device="cuda")
     d_s = torch.empty((n, 4), dtype=torch.int64, device="cuda")
     _lib.check(L.b200_gen_bases_dev(cid, 5, n, d_bases.data_ptr(), d_b.data_ptr(), st))
-    _lib.check(L.b200_gen_scalars_dev(cid, 6, n, d_s.data_ptr(), st))
+    _lib.check(L.b200_gen_scalars_dev(1 if cid == 1 else 0, 6, n, d_s.data_ptr(), st))   # scalar field: BN254 Fr for BN254, BLS12-381 Fr otherwise
     ref = None
     for c in (0, 3, 7, 12):
         VB.set_window(c)

@@ -178,6 +178,7 @@ struct EnvKnobs {
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
     double level_min_load = 16.0;         // automatic mode: keep adding affine levels while the average bucket still holds this many entries
     int level_cap = 8;                    // upper bound on top of the per-curve LEVEL_CAP
+    int pad_bases = 0;                    // level 1 gathers from a copy of the bases padded to one 128-byte line per point (BLS12-381 G1)
     int stagger = 0;                      // generation-2 pair-add: unequal batches inside groups of four blocks (desynchronises the inversions)
     int reduce_log_m = 6;                 // buckets per reduction thread = 2^reduce_log_m at most
     bool reduce_log_m_forced = false;     // set through the environment: used as given (tuning runs)
@@ -193,6 +194,7 @@ struct EnvKnobs {
         if (const char *e = getenv("B200_MSM_LEVEL_MIN_LOAD")) level_min_load = std::max(2.0, atof(e));
         if (const char *e = getenv("B200_MSM_LEVEL_CAP")) level_cap = std::min(8, std::max(0, atoi(e)));
         if (const char *e = getenv("B200_MSM_STAGGER")) stagger = atoi(e) != 0;
+        if (const char *e = getenv("B200_MSM_PAD_BASES")) pad_bases = atoi(e) != 0;
         if (const char *e = getenv("B200_MSM_REDUCE_LOG_M")) { reduce_log_m = std::min(8, std::max(0, atoi(e))); reduce_log_m_forced = true; }
         if (const char *e = getenv("B200_MSM_FORCE_CHUNKS")) force_chunks = atoi(e);
         if (const char *e = getenv("B200_L2_FETCH_GRANULARITY")) l2_fetch_granularity = atoi(e);
@@ -438,7 +440,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
     }
 
     // batched-affine levels + XYZZ accumulation of the buckets [b0, b1) (a group of whole windows) of the current chunk
-    int reduce_group(const uint32_t *bas, size_t b0, size_t b1, size_t group_entries, int levels, uint32_t *target) {
+    int reduce_group(const uint32_t *bas, const uint32_t *bas_padded, size_t b0, size_t b1, size_t group_entries, int levels, uint32_t *target) {
         const size_t nbg = b1 - b0;
         const bool forced = levels_opt >= 0;
         size_t cur_entries = group_entries;   // upper bound on the entries of the current level
@@ -471,7 +473,10 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 msm_pairmap_kernel<<<(unsigned)((out_cap + 1023) / 1024), 256, 0, st>>>(cur_offsets, off2, (uint32_t)nbg, pairmap);
                 AB_LAUNCHED();
             }
-            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts, env_knobs().shared_inv, (variant == 2 && env_knobs().shared_inv) ? env_knobs().stagger : 0, st)) return rc;
+            const bool padded = lv == 0 && variant == 2 && bas_padded;
+            if (int rc = MsmPairLaunch<C>::run(variant, lv == 0, padded ? bas_padded : bas, cur_src, cur_offsets, off2, pairmap, (uint32_t)nbg, batch, out_cap, pts,
+                                               env_knobs().shared_inv, (variant == 2 && env_knobs().shared_inv) ? env_knobs().stagger : 0, padded ? 32u : 0u, st))
+                return rc;
             arena.release(pairmap);
             // the level before the previous one is no longer read
             arena.release(lvl_pts[lv & 1]);
@@ -551,11 +556,17 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 gw = std::min(g.W, gw);
                 const int ngroups = (g.W + gw - 1) / gw;
                 gw = (g.W + ngroups - 1) / ngroups;
+                uint32_t *bas_padded = nullptr;
+                if (env_knobs().pad_bases && env_knobs().pair_variant_l1 == 2 && 2 * L * 4 < 128) {
+                    if (int rc = arena.alloc(&bas_padded, nk * 128)) return rc;
+                    if (int rc = MsmPairLaunch<C>::pad_bases(bas, nk, bas_padded, st)) return rc;
+                }
                 for (int w0 = 0; w0 < g.W; w0 += gw) {
                     const int w1 = std::min(g.W, w0 + gw);
                     const size_t b0 = (size_t)w0 * g.nb, b1 = (w1 == g.W) ? nb_total : (size_t)w1 * g.nb;
-                    if (int rc = reduce_group(bas, b0, b1, nk * (size_t)(w1 - w0), levels, target)) return rc;
+                    if (int rc = reduce_group(bas, bas_padded, b0, b1, nk * (size_t)(w1 - w0), levels, target)) return rc;
                 }
+                arena.release(bas_padded);
             }
         }
         if (chunks_done > 0) {

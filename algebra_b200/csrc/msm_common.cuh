@@ -78,7 +78,9 @@ template <int L> __device__ __forceinline__ void store_xyzz(uint32_t *p, const X
 template <class C> struct MsmPairLaunch {
     // one batched-affine level over the buckets [0, nbg): variant 1 = thread-contiguous batches, 2 = warp-interleaved + cp.async
     static int run(int variant, bool first, const uint32_t *bases, const uint32_t *src, const uint32_t *offsets_in, const uint32_t *offsets_out,
-                   const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, int stagger, cudaStream_t st);
+                   const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, int stagger, uint32_t base_stride, cudaStream_t st);
+    // copy of the bases with one point per 128-byte line (base_stride = 32 words); only for points of <= 128 bytes
+    static int pad_bases(const uint32_t *bases, size_t n, uint32_t *padded, cudaStream_t st);
 };
 template <class C> struct MsmAccLaunch {
     static int digits(int mode, const void *scalars, int kind, size_t nk, MsmGeom g, int w0, int w1, uint32_t *counts_or_cursor, uint32_t *sorted,

@@ -1,17 +1,18 @@
 // msm_k_pair.cuh — batched-affine pair-add kernels (both generations) and their launcher.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "msm_common.cuh"
 
 namespace ab200 {
 
 template <class F, bool FIRST>
 __device__ __forceinline__ void pair_load_point(uint32_t *x, uint32_t *y, const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
-                                                uint32_t k) {
+                                                uint32_t k, uint32_t base_stride = 2 * F::L) {
     constexpr int L = F::L;
     if (FIRST) {
         const uint32_t e = __ldg(src + k);
-        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * (2 * L);
+        const uint32_t *bp = bases + (size_t)(e & 0x7fffffffu) * base_stride;
         load_limbs_nc<L>(x, bp);
         load_limbs_nc<L>(y, bp + L);
         F::cneg(y, y, (e >> 31) != 0);   // -(0,0) stays (0,0)
@@ -280,7 +281,8 @@ template <int L> __device__ __forceinline__ void strip_read(uint32_t *r, const u
 template <class C, bool FIRST, int MINB>
 __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t *__restrict__ bases, const uint32_t *__restrict__ src,
                                                                 const uint32_t *__restrict__ pairmap, const uint32_t *__restrict__ offsets_out,
-                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out, int shared_inv, int stagger) {
+                                                                uint32_t nb, uint32_t batch, uint32_t *__restrict__ out, int shared_inv, int stagger,
+                                                                uint32_t base_stride) {
     using F = typename C::F;
     constexpr int L = F::L;
     uint64_t stagger_base = 0;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
     const uint32_t cnt = active ? (w_hi - p0 + 31) >> 5 : 0;   // slots p0 + 32*i, i < cnt
     // address of the point behind input entry `k` (FIRST: through the sorted index, e = index | sign << 31)
     auto point = [&](uint32_t k, uint32_t e) -> const uint32_t * {
-        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * L) : src + (size_t)k * (2 * L);
+        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * base_stride : src + (size_t)k * (2 * L);   // base_stride: 2L words, or 32 (padded to a line)
     };
     uint32_t x1[L], y1[L], x2[L], y2[L], den[L], run[L];
     // software pipeline over the slots of this lane: (m, e1, e2) describe a slot (pairmap word and, for FIRST, the two sorted
@@ -342,8 +344,8 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
         if (has2) {
             if (limbs_is_zero<L>(x1) || limbs_is_zero<L>(x2) || limbs_eq<L>(x1, x2)) {   // rare: identity operand / equal x
                 const uint32_t k = m_c & 0x7fffffffu;
-                pair_load_point<F, FIRST>(x1, y1, bases, src, k);
-                pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1);
+                pair_load_point<F, FIRST>(x1, y1, bases, src, k, base_stride);
+                pair_load_point<F, FIRST>(x2, y2, bases, src, k + 1, base_stride);
                 const int kind = pair_classify<F>(den, x1, y1, x2, y2, true);
                 if (kind >= PAIR_ADD) F::mul(run, run, den);
             } else {
@@ -443,10 +445,32 @@ __global__ void __launch_bounds__(128, MINB) msm_pair_add2_kernel(const uint32_t
     }
 }
 
+// bases (2L words each, dense) -> one point per 128-byte line (G1 of BLS12-381: 96 -> 128 bytes): a level-1 gather then touches exactly
+// one line instead of 1.5 on average
+template <int L> __global__ void __launch_bounds__(256) msm_pad_bases_kernel(const uint4 *__restrict__ in, size_t n, uint4 *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int j = 0; j < 2 * L / 4; j++) out[i * 8 + j] = __ldg(in + i * (2 * L / 4) + j);
+}
+template <class C> int MsmPairLaunch<C>::pad_bases(const uint32_t *bases, size_t n, uint32_t *padded, cudaStream_t st) {
+    constexpr int L = C::F::L;
+    if constexpr (2 * L * 4 <= 128) {
+        msm_pad_bases_kernel<L><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint4 *)bases, n, (uint4 *)padded);
+        AB_LAUNCHED();
+        return 0;
+    } else {
+        set_last_error("pad_bases: points larger than one line");
+        return B200_EINVAL;
+    }
+}
+
 template <class C>
 int MsmPairLaunch<C>::run(int variant, bool first, const uint32_t *bases, const uint32_t *src, const uint32_t *offsets_in, const uint32_t *offsets_out,
-                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, int stagger, cudaStream_t st) {
+                          const uint32_t *pairmap, uint32_t nbg, uint32_t batch, size_t out_cap, uint32_t *out, int shared_inv, int stagger, uint32_t base_stride, cudaStream_t st) {
     constexpr int L = C::F::L;
+    if (!base_stride) base_stride = 2 * L;
+    static const int l1_minb = [] { const char *e = getenv("B200_MSM_L1_MINB"); return e ? atoi(e) : 4; }();
     if (variant == 2) {
         unsigned pg;
         if (stagger) {   // groups of four blocks with batches b, 0.85 b, 0.7 b, 0.55 b (see the kernel)
@@ -457,12 +481,15 @@ int MsmPairLaunch<C>::run(int variant, bool first, const uint32_t *bases, const 
             pg = (unsigned)((warps + 3) / 4);
         }
         const size_t smem = (size_t)5 * (L / 4) * 128 * 16;
-        if (first) {
+        if (first && l1_minb == 5 && C::PAIR_MINB == 4) {   // experiment: level 1 with 5 resident blocks (<= 102 registers)
+            AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, true, C::PAIR_MINB + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            msm_pair_add2_kernel<C, true, C::PAIR_MINB + 1><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger, base_stride);
+        } else if (first) {
             AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, true, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger);
+            msm_pair_add2_kernel<C, true, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger, base_stride);
         } else {
             AB_CUDA(cudaFuncSetAttribute(msm_pair_add2_kernel<C, false, C::PAIR_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger);
+            msm_pair_add2_kernel<C, false, C::PAIR_MINB><<<pg, 128, smem, st>>>(bases, src, pairmap, offsets_out, nbg, batch, out, shared_inv, stagger, base_stride);
         }
     } else {
         const uint32_t nthreads = (uint32_t)((out_cap + batch - 1) / batch);

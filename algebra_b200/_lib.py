@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200_msm_stream_abort": (_c.c_int, [_vp]),
     "b200_set_msm_window": (_c.c_int, [_c.c_int]),
     "b200_set_msm_affine_levels": (_c.c_int, [_c.c_int]),
+    "b200_set_msm_bucket_slice": (_c.c_int, [_c.c_int, _c.c_int]),
     "b200_msm_window_for": (_c.c_int, [_c.c_int, _c.c_size_t]),
     "b200_g1_sum": (_c.c_int, [_c.c_int, _vp, _c.c_size_t, _vp]),
     "b200_g1_into_affine": (_c.c_int, [_c.c_int, _vp, _vp]),

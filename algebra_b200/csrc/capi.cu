@@ -29,6 +29,8 @@ int msm_set_window(int c);
 int msm_set_affine_levels(int levels);
 int msm_get_window();
 int msm_get_affine_levels();
+int msm_set_bucket_slice(int slice, int slices);
+void msm_get_bucket_slice(int *slice, int *slices);
 int msm_auto_window(size_t n, int scalar_bits);
 int msm_last_timings(float *ms7, int *c, int *windows, unsigned long long *bucket_adds);
 int g1_sum_dispatch(int curve, const uint64_t *pts_host, size_t k, uint64_t *out_host, bool to_affine);
@@ -252,10 +254,14 @@ template <class Fn> static int per_device(int ngpus, Fn fn) {
     };
     int dev0 = 0;
     cudaGetDevice(&dev0);
+    int slice = 0, slices = 1;   // input-chunk sharding computes whole MSMs: the caller's bucket slice does not apply here
+    msm_get_bucket_slice(&slice, &slices);
+    msm_set_bucket_slice(0, 1);
     std::vector<std::thread> th;
     for (int d = 1; d < ngpus; d++) th.emplace_back(body, d);
     body(0);
     for (auto &t : th) t.join();
+    msm_set_bucket_slice(slice, slices);
     cudaSetDevice(dev0);
     for (int d = 0; d < ngpus; d++)
         if (rc[d]) { set_last_error("device " + std::to_string(d) + ": " + msg[d]); return rc[d]; }
@@ -470,6 +476,7 @@ int b200_msm_stream_finish(b200_msm_stream_t *s, uint64_t *out_xyz) {
 
 int b200_set_msm_window(int c) { return msm_set_window(c); }
 int b200_set_msm_affine_levels(int levels) { return msm_set_affine_levels(levels); }
+int b200_set_msm_bucket_slice(int slice, int slices) { return msm_set_bucket_slice(slice, slices); }
 int b200_msm_window_for(int curve, size_t n) {
     if (!msm_coord_words(curve)) return B200_EINVAL;
     return msm_auto_window(n, curve == B200_CURVE_BN254 ? 254 : 255);

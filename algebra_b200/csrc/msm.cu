@@ -176,6 +176,8 @@ struct EnvKnobs {
                                           // 10 groups (8 GB) 392 ms — groups shorten the batches of the later levels
     int shared_inv = 1;                   // one field inversion per block (Montgomery's trick across the block) instead of per thread
     int min_batch = 256;                  // automatic mode: shortest per-thread batch a level may run with
+    int target_waves = 1;                 // a level is cut into at least this many waves of resident blocks (when batches stay >= wave_min_batch)
+    int wave_min_batch = 192;
     double level_min_load = 16.0;         // automatic mode: keep adding affine levels while the average bucket still holds this many entries
     int level_cap = 8;                    // upper bound on top of the per-curve LEVEL_CAP
     int pad_bases = 0;                    // level 1 gathers from a copy of the bases padded to one 128-byte line per point (BLS12-381 G1)
@@ -191,6 +193,8 @@ struct EnvKnobs {
         if (const char *e = getenv("B200_MSM_SHARED_INV")) shared_inv = atoi(e) != 0;
         min_batch = shared_inv ? 96 : 256;   // overhead per addition: 590/(4*batch) multiplications shared, 570/batch per thread
         if (const char *e = getenv("B200_MSM_MIN_BATCH")) min_batch = std::max(8, atoi(e));
+        if (const char *e = getenv("B200_MSM_TARGET_WAVES")) target_waves = std::max(1, atoi(e));
+        if (const char *e = getenv("B200_MSM_WAVE_MIN_BATCH")) wave_min_batch = std::max(8, atoi(e));
         if (const char *e = getenv("B200_MSM_LEVEL_MIN_LOAD")) level_min_load = std::max(2.0, atof(e));
         if (const char *e = getenv("B200_MSM_LEVEL_CAP")) level_cap = std::min(8, std::max(0, atoi(e)));
         if (const char *e = getenv("B200_MSM_STAGGER")) stagger = atoi(e) != 0;
@@ -207,6 +211,7 @@ static const EnvKnobs &env_knobs() {
 
 static thread_local int t_window_override = 0;
 static thread_local int t_affine_levels = -1;   // batched-affine pre-reduction levels; -1 = automatic
+static thread_local int t_slice = 0, t_slices = 1;   // bucket slice computed by this thread's MSMs (make_geom)
 struct MsmTimings {
     float ms[7] = {0, 0, 0, 0, 0, 0, 0};
     int c = 0, W = 0;
@@ -220,6 +225,13 @@ int msm_set_affine_levels(int levels) {
     return 0;
 }
 
+int msm_set_bucket_slice(int slice, int slices) {
+    if (slices < 1 || slices > 64 || slice < 0 || slice >= slices) { set_last_error("bucket slice must satisfy 0 <= slice < slices <= 64"); return B200_EINVAL; }
+    t_slice = slice;
+    t_slices = slices;
+    return 0;
+}
+void msm_get_bucket_slice(int *slice, int *slices) { *slice = t_slice; *slices = t_slices; }
 int msm_get_window() { return t_window_override; }
 int msm_get_affine_levels() { return t_affine_levels; }
 int msm_set_window(int c) {
@@ -353,6 +365,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
     uint32_t *buckets = nullptr, *extra = nullptr;
     size_t scan_blocks = 0;
     int restore_l2_gran = -1;
+    bool sliced = false;   // bucket slice of a larger MSM: entry counts are read back per chunk (they are ~1/slices of the bound)
 
     int coord_words() const override { return L; }
 
@@ -371,7 +384,8 @@ template <class C> struct MsmSession final : MsmSessionBase {
         scalar_bytes = scalar_kind_bytes(kind);
         int c = t_window_override ? t_window_override : msm_auto_window(std::max(n_total, max_chunk), scalar_bits);
         if (c > scalar_bits) c = scalar_bits;
-        g = make_geom(c, scalar_bits);
+        g = make_geom(c, scalar_bits, t_slice, t_slices);
+        sliced = t_slices > 1;
         const size_t nb_total = g.total_buckets;
         const size_t max_entries = max_chunk * (size_t)g.W;
         if (max_entries >= ((size_t)1 << 31)) { set_last_error("chunk pairs * windows must be < 2^31"); return B200_ETOOLARGE; }
@@ -457,7 +471,11 @@ template <class C> struct MsmSession final : MsmSessionBase {
             const double per_lane = (double)out_cap / lanes_per_wave;
             const double min_batch = (double)env_knobs().min_batch;
             if (!forced && per_lane < min_batch) break;
-            const double waves = std::max(1.0, std::ceil(per_lane / 1024.0));
+            double waves = std::max(1.0, std::ceil(per_lane / 1024.0));
+            // a single wave runs every block through the same phase (gather, multiply, invert) at the same time; several shorter
+            // waves let the memory-bound and the arithmetic phases of different blocks overlap
+            if ((double)env_knobs().target_waves > waves)
+                waves = std::max(waves, std::min((double)env_knobs().target_waves, std::floor(per_lane / (double)env_knobs().wave_min_batch)));
             uint32_t batch = (uint32_t)std::ceil((double)out_cap / (waves * lanes_per_wave));
             batch = std::min(1024u, std::max(forced ? 8u : (uint32_t)min_batch, batch));
             uint32_t *pts = nullptr, *off2 = nullptr;
@@ -511,47 +529,62 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 if (int rc = arena.alloc(&extra, nb_total * 4 * L * 4)) return rc;
             target = extra;
         }
+        if (nb_total == 0) nk = 0;   // slice without buckets (a window with fewer buckets than slices goes whole to slice 0)
         AB_CUDA(cudaEventRecord(e[0], st));
         AB_CUDA(cudaMemsetAsync(counts, 0, nb_total * 4, st));
         if (nk)
             if (int rc = MsmAccLaunch<C>::digits(0, d_scalars, kind, nk, g, 0, g.W, counts, nullptr, st)) return rc;
         AB_CUDA(cudaEventRecord(e[1], st));
-        if (int rc = scan(counts, nb_total, offsets)) return rc;
+        if (nb_total)
+            if (int rc = scan(counts, nb_total, offsets)) return rc;
         AB_CUDA(cudaMemcpyAsync(cursor, offsets, nb_total * 4, cudaMemcpyDeviceToDevice, st));
+        // entries of the chunk up to each window boundary: the bound nk per window, or — for a bucket slice, which receives only
+        // ~1/slices of it — the counts themselves (one small read-back per chunk; the launch geometry of the levels depends on it)
+        std::vector<size_t> upto((size_t)g.W + 1);
+        for (int w = 0; w <= g.W; w++) upto[w] = nk * (size_t)w;
+        if (sliced && nk) {
+            std::vector<uint32_t> h((size_t)g.W + 1, 0u);
+            for (int w = 1; w <= g.W; w++)
+                AB_CUDA(cudaMemcpyAsync(&h[w], offsets + (w == g.W ? nb_total : (size_t)w * g.nb), 4, cudaMemcpyDeviceToHost, st));
+            AB_CUDA(cudaStreamSynchronize(st));
+            for (int w = 0; w <= g.W; w++) upto[w] = h[w];
+        }
+        const size_t entries = upto[g.W];
         AB_CUDA(cudaEventRecord(e[2], st));
         // scatter in groups of windows so that the active write fronts (one 32-byte sector per bucket of the group) stay
         // L2-resident: random 4-byte stores into a multi-GB array otherwise cost a DRAM sector each (measured 2.5x slower)
         if (nk) {
-            const size_t front_bytes = (size_t)g.nb * 32;
+            const size_t front_bytes = std::max<size_t>(g.nb, 1) * 32;
             const int group = (int)std::max<size_t>(1, ((size_t)48 << 20) / front_bytes);
             for (int w0 = 0; w0 < g.W; w0 += group)
                 if (int rc = MsmAccLaunch<C>::digits(1, d_scalars, kind, nk, g, w0, std::min(g.W, w0 + group), cursor, sorted, st)) return rc;
         }
         AB_CUDA(cudaEventRecord(e[3], st));
         AB_CUDA(cudaMemsetAsync(target, 0, nb_total * 4 * L * 4, st));
-        if (nk) {
+        if (nk && entries) {
             // batched-affine levels: automatic = keep halving while buckets still hold >= ~8 entries, at most 4 levels
             // (measured at 2^26: 339 / 324 / 310 / 303 / 300 ms of accumulation for 0..4 levels)
             int levels = levels_opt;
             if (levels < 0) {
                 levels = 0;
                 if (C::AUTO_LEVELS)
-                    for (double l = (double)nk / (double)g.nb; l >= env_knobs().level_min_load && levels < std::min(env_knobs().level_cap, C::LEVEL_CAP); l *= 0.5) levels++;
+                    for (double l = (double)nk / (double)(1u << (g.c - 1)); l >= env_knobs().level_min_load && levels < std::min(env_knobs().level_cap, C::LEVEL_CAP); l *= 0.5) levels++;
                 // the first level must be able to give every resident thread a batch of >= 256 additions
-                if ((double)nk * g.W * 0.5 / ((double)sm_count() * C::PAIR_MINB * 128.0) < (double)env_knobs().min_batch) levels = 0;
+                if ((double)entries * 0.5 / ((double)sm_count() * C::PAIR_MINB * 128.0) < (double)env_knobs().min_batch) levels = 0;
             }
             if (levels == 0) {
-                if (int rc = accumulate(bas, sorted, offsets, nb_total, nk * (size_t)g.W, target)) return rc;
+                if (int rc = accumulate(bas, sorted, offsets, nb_total, entries, target)) return rc;
             } else {
                 // window groups: the level arrays of one group (level 1: entries/2 affine points, level 2: half of that, two
                 // levels alive at a time) must fit the scratch budget; groups are whole windows, balanced in size
-                const double per_window = ((double)nk * 0.5 + (double)g.nb * 0.5) * 2 * L * 4 * 1.5 + (double)nk * 0.5 * 4;
+                const double ew = (double)entries / g.W;   // entries per window
+                const double per_window = (ew * 0.5 + (double)g.nb * 0.5) * 2 * L * 4 * 1.5 + ew * 0.5 * 4;
                 double budget = env_knobs().level_budget_bytes;
                 size_t free_b = 0, total_b = 0;
                 if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min(budget, 0.6 * (double)free_b + pool_reserved_bytes());
                 int gw = (int)std::floor(budget / per_window);
                 // ... and a group must give every resident thread a batch of >= min_batch additions at level 1
-                const int gw_min = (int)std::ceil((double)env_knobs().min_batch * (double)sm_count() * C::PAIR_MINB * 128.0 / ((double)nk * 0.5));
+                const int gw_min = (int)std::ceil((double)env_knobs().min_batch * (double)sm_count() * C::PAIR_MINB * 128.0 / std::max(1.0, ew * 0.5));
                 gw = std::max(std::max(1, gw_min), std::min(g.W, gw));
                 gw = std::min(g.W, gw);
                 const int ngroups = (g.W + gw - 1) / gw;
@@ -564,7 +597,7 @@ template <class C> struct MsmSession final : MsmSessionBase {
                 for (int w0 = 0; w0 < g.W; w0 += gw) {
                     const int w1 = std::min(g.W, w0 + gw);
                     const size_t b0 = (size_t)w0 * g.nb, b1 = (w1 == g.W) ? nb_total : (size_t)w1 * g.nb;
-                    if (int rc = reduce_group(bas, bas_padded, b0, b1, nk * (size_t)(w1 - w0), levels, target)) return rc;
+                    if (int rc = reduce_group(bas, bas_padded, b0, b1, upto[w1] - upto[w0], levels, target)) return rc;
                 }
                 arena.release(bas_padded);
             }
@@ -595,7 +628,8 @@ template <class C> struct MsmSession final : MsmSessionBase {
         if (int rc = arena.alloc(&partials, (size_t)g.W * chunks * 4 * L * 4)) return rc;
         if (int rc = arena.alloc(&partials2, (size_t)g.W * 32 * 4 * L * 4)) return rc;
         if (int rc = arena.alloc(&window_sums, (size_t)g.W * 4 * L * 4)) return rc;
-        if (int rc = MsmRedLaunch<C>::reduce(buckets, g, log_m, chunks, partials, partials2, window_sums, st)) return rc;
+        if (nb_total == 0) AB_CUDA(cudaMemsetAsync(window_sums, 0, (size_t)g.W * 4 * L * 4, st));   // empty slice: the identity
+        else if (int rc = MsmRedLaunch<C>::reduce(buckets, g, log_m, chunks, partials, partials2, window_sums, st)) return rc;
         AB_CUDA(cudaEventRecord(e_red, st));
         if (int rc = MsmRedLaunch<C>::combine(window_sums, g.W, g.c, d_out, st)) return rc;
         AB_CUDA(cudaEventRecord(e_end, st));

@@ -42,18 +42,29 @@ struct CurveBlsG2 {
 
 struct MsmGeom {
     int c, W, top_bits;          // window bits, number of windows, bits in the top window
-    uint32_t nb;                 // buckets per non-top window = 2^(c-1)
-    uint32_t nb_top;             // buckets in the top window   = 2^top_bits
+    uint32_t nb;                 // buckets of this slice per non-top window (whole window: 2^(c-1))
+    uint32_t nb_top;             // buckets of this slice in the top window  (whole window: 2^top_bits)
     uint32_t total_buckets;      // (W-1)*nb + nb_top
+    uint32_t off, off_top;       // first bucket of the slice inside a non-top / the top window (0 for the whole window)
 };
 
-inline MsmGeom make_geom(int c, int scalar_bits) {
+// Bucket slice `slice` of `slices`: every window keeps the contiguous range [nbw*slice/slices, nbw*(slice+1)/slices) of its
+// buckets (bucket j of a window has weight j+1, so a slice's sums carry `off` as an extra chunk offset in the reduction) and
+// the slices' results add up to the complete MSM.  A window with fewer buckets than slices is given whole to slice 0.
+inline MsmGeom make_geom(int c, int scalar_bits, int slice = 0, int slices = 1) {
     MsmGeom g;
     g.c = c;
     g.W = (scalar_bits + c - 1) / c;  // digits_count (:452)
     g.top_bits = scalar_bits - (g.W - 1) * c;
-    g.nb = 1u << (c - 1);
-    g.nb_top = 1u << g.top_bits;
+    const uint32_t full = 1u << (c - 1), full_top = 1u << g.top_bits;
+    auto cut = [&](uint32_t nbw, int i) -> uint32_t {
+        if (nbw < (uint32_t)slices) return i == 0 ? 0u : nbw;
+        return (uint32_t)((uint64_t)nbw * (uint64_t)i / (uint64_t)slices);
+    };
+    g.off = cut(full, slice);
+    g.nb = cut(full, slice + 1) - g.off;
+    g.off_top = cut(full_top, slice);
+    g.nb_top = cut(full_top, slice + 1) - g.off_top;
     g.total_buckets = (uint32_t)(g.W - 1) * g.nb + g.nb_top;
     return g;
 }

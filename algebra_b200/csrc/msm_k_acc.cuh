@@ -56,8 +56,10 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void *__restrict_
             if (carry) { mag = (1u << c) - coef; neg = 1; }  // digit = coef - 2^c in [-2^(c-1), 0)
             else mag = coef;
         }
-        if (mag && w >= w_lo) {
-            uint32_t gid = (uint32_t)w * g.nb + (mag - 1);
+        // bucket slice: only the magnitudes in [off, off + nbw) of each window belong to this session (whole window by default)
+        const uint32_t rel = mag - 1 - ((w == g.W - 1) ? g.off_top : g.off);
+        if (mag && w >= w_lo && rel < ((w == g.W - 1) ? g.nb_top : g.nb)) {
+            uint32_t gid = (uint32_t)w * g.nb + rel;
             if (MODE == 0) {
                 atomicAdd(&counts_or_cursor[gid], 1u);
             } else {

@@ -7,7 +7,8 @@ namespace ab200 {
 // ------------------------------------------------------------------------------------------------
 // bucket reduction.  Window w needs S_w = sum_j (j+1) * B_w[j]  (:478-484).  Thread t of a window takes buckets
 // [t*m, (t+1)*m): running sum gives  sum_l (l+1)*B[t*m+l]  and the chunk total R_t; adding (t*m) * R_t (double-and-add)
-// makes its contribution complete.  partial index = window * chunks_stride + t.
+// makes its contribution complete (for a bucket slice starting at bucket `off` of the window: (off + t*m) * R_t).
+// partial index = window * chunks_stride + t.
 // ------------------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const uint32_t *__restrict__ buckets, MsmGeom g, int log_m,
@@ -33,13 +34,14 @@ __global__ void __launch_bounds__(128) msm_bucket_reduce_kernel(const uint32_t *
             E::xyzz_add(run, b);
             E::xyzz_add(sum, run);
         }
-        // sum += lo * run
-        if (lo != 0 && !E::xyzz_is_zero(run)) {
+        // sum += (lo + first bucket of the slice) * run
+        const uint32_t wlo = lo + ((w == (uint32_t)g.W - 1) ? g.off_top : g.off);
+        if (wlo != 0 && !E::xyzz_is_zero(run)) {
             typename E::B acc;
             E::xyzz_set_zero(acc);
-            for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+            for (int bit = 31 - __clz(wlo); bit >= 0; bit--) {
                 if (!E::xyzz_is_zero(acc)) E::xyzz_dbl(acc);
-                if ((lo >> bit) & 1) E::xyzz_add(acc, run);
+                if ((wlo >> bit) & 1) E::xyzz_add(acc, run);
             }
             E::xyzz_add(sum, acc);
         }

@@ -1,9 +1,16 @@
-"""Multi-GPU MSM: input-chunk sharding + one exchange of a partial point per rank.
+"""Multi-GPU MSM: input-chunk or bucket-slice sharding + one exchange of a partial point per rank.
 
 sum_i s_i*P_i splits over any partition of i, so each rank runs the complete single-GPU MSM on its contiguous chunk
 and the only communication is an all-gather of one Jacobian point (3N u64 = 144 B for BLS12-381) per rank over
 NCCL/NVLink, followed by k-1 point additions on every rank — NCCL cannot reduce curve points, so all-gather + local
 sum *is* the all-reduce.  The NTT is not sharded ("replicas only").
+
+Two partitions of the same sum:
+  * input chunks (`msm_sharded`, `msm_global`): rank r owns the pairs [lo_r, hi_r) — nothing is replicated, the right split
+    when the inputs start on the host (each GPU receives 1/world of the bytes); every rank repeats the per-bucket reduction;
+  * bucket slices (`msm_bucket_sliced`): every rank holds ALL pairs (an SRS replicated in every GPU's HBM, scalars produced on
+    or broadcast to the devices) and owns the buckets [nb*r/world, nb*(r+1)/world) of every window — sort, accumulation AND
+    bucket reduction all shrink by 1/world, only the digit extraction is repeated.
 
 One process per GPU, `torch.distributed` for the plumbing (backend nccl on GPUs; gloo works for the host logic).
 `local_msm` / `sum_fn` default to the CUDA library; tests inject CPU stand-ins to exercise the plumbing without a GPU."""
@@ -49,6 +56,32 @@ def msm_sharded(curve: G1Curve | int, local_bases, local_scalars, group=None, lo
     device = None
     if type(local_bases).__module__.startswith("torch") and local_bases.is_cuda:
         device = local_bases.device
+    return sum_fn(all_gather_points(partial, group, device))
+
+
+def msm_bucket_sliced(curve: G1Curve | int, bases, scalars, group=None, local_msm=None, sum_fn=None) -> np.ndarray:
+    """MSM over (bases, scalars) present in full on every rank; rank r computes bucket slice r of world (all windows), the
+    partial points are all-gathered and summed.  `local_msm(bases, scalars, slice, slices)` defaults to the CUDA library."""
+    import torch.distributed as dist
+    from . import variable_base as VB
+    cv = CURVES[curve] if isinstance(curve, int) else curve
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def cuda_slice(b, s, i, k):
+        VB.set_bucket_slice(i, k)
+        try:
+            return VB.msm_unchecked(cv, b, s)
+        finally:
+            VB.set_bucket_slice(0, 1)
+
+    partial = (local_msm or cuda_slice)(bases, scalars, rank, world)
+    if world == 1:
+        return partial
+    sum_fn = sum_fn or (lambda pts: VB.sum_points(cv, pts))
+    device = None
+    if type(bases).__module__.startswith("torch") and bases.is_cuda:
+        device = bases.device
     return sum_fn(all_gather_points(partial, group, device))
 
 

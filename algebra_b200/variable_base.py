@@ -257,6 +257,12 @@ def set_affine_levels(levels: int) -> None:
     _lib.check(_lib.lib().b200_set_msm_affine_levels(levels))
 
 
+def set_bucket_slice(slice_index: int = 0, slices: int = 1) -> None:
+    """restrict this thread's single-device MSMs to bucket slice `slice_index` of `slices` (include/algebra_b200.h:
+    b200_set_msm_bucket_slice); the `slices` partial results over the same inputs add up to the msm.  (0, 1) = whole MSM"""
+    _lib.check(_lib.lib().b200_set_msm_bucket_slice(slice_index, slices))
+
+
 def window_for(curve: G1Curve | int, n: int) -> int:
     cv = CURVES[curve] if isinstance(curve, int) else curve
     return _lib.lib().b200_msm_window_for(cv.cid, n)

@@ -7,9 +7,10 @@ the reference.  Contract: one JSON line on stdout (rank 0).
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full MSM over n = 2^26 synthetic (base, scalar) pairs (bases P_i = b_i*G generated on the device,
-uniform scalars); with N > 1 the pairs are sharded by contiguous chunk, each rank runs the whole single-GPU MSM on
-its chunk, one NCCL all-gather exchanges a partial point per rank and every rank adds the N points ("strong"
-scaling: total work fixed).  The NTT leg (n = 2^24, forward) is timed the same way right after and reported under
+uniform scalars); with N > 1 the MSM shards with no data-path collective: the device-resident leg by bucket slices
+(every rank holds all pairs and owns 1/N of every window's buckets; --shard chunks: contiguous input chunks), the
+host-buffer leg by input chunks; one NCCL all-gather exchanges a partial point per rank and every rank adds the N
+points ("strong" scaling: total work fixed).  The NTT leg (n = 2^24, forward) is timed the same way right after and reported under
 "ntt" ("replicas only": with N > 1 every rank transforms its own vector).
 `value` has inputs resident in HBM; `e2e` goes through the host-buffer C-ABI call (H2D of bases+scalars from pinned
 host memory and D2H of the result inside the timed region)."""
@@ -187,6 +188,8 @@ def main():
     ap.add_argument("--curve", type=int, default=0, help="0 = BLS12-381 G1 (metric), 1 = BN254 G1")
     ap.add_argument("--window", type=int, default=0, help="Pippenger window override (0 = auto)")
     ap.add_argument("--affine-levels", type=int, default=-1, help="batched-affine pre-reduction levels (-1 = auto)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "buckets", "chunks"],
+                    help="N > 1, device-resident leg: bucket slices over replicated inputs (auto) or input chunks")
     ap.add_argument("--seed", type=int, default=20260922)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,7 +218,15 @@ def main():
     cv = ab.params.CURVES[args.curve]
     N = cv.N
     n_total = 1 << args.log_n_msm
-    n_local = n_total // world
+    # N > 1, device-resident leg: "buckets" = every rank holds all n pairs (replicated, as an SRS is) and owns 1/N of every
+    # window's buckets; "chunks" = rank r holds and processes the pairs [n*r/N, n*(r+1)/N).  The host-buffer (e2e) leg always
+    # ships chunks: each GPU then receives 1/N of the bytes.
+    shard = args.shard if world > 1 else "chunks"
+    if shard == "auto":
+        shard = "buckets"
+    n_chunk = n_total // world
+    n_local = n_total if shard == "buckets" else n_chunk
+    c_lo = rank * n_chunk if shard == "buckets" else 0     # this rank's chunk inside its resident arrays
     st = torch.cuda.current_stream().cuda_stream
     hbm_peak, peak_src = measured_peaks()
 
@@ -236,8 +247,9 @@ def main():
     d_bases = torch.empty((n_local, 2 * N), dtype=torch.int64, device=dev)
     d_b = torch.empty((n_local,), dtype=torch.int64, device=dev)
     d_scal = torch.empty((n_local, 4), dtype=torch.int64, device=dev)
-    _lib.check(L.b200_gen_bases_dev(cv.cid, args.seed + 1000 * rank, n_local, d_bases.data_ptr(), d_b.data_ptr(), st))
-    _lib.check(L.b200_gen_scalars_dev(cv.ntt_field_id, args.seed + 7777 + 1000 * rank, n_local, d_scal.data_ptr(), st))
+    gen_seed = args.seed + (0 if shard == "buckets" else 1000 * rank)    # replicated inputs: the same stream on every rank
+    _lib.check(L.b200_gen_bases_dev(cv.cid, gen_seed, n_local, d_bases.data_ptr(), d_b.data_ptr(), st))
+    _lib.check(L.b200_gen_scalars_dev(cv.ntt_field_id, gen_seed + 7777, n_local, d_scal.data_ptr(), st))
     VB.set_window(args.window)
     VB.set_affine_levels(args.affine_levels)
 
@@ -246,6 +258,8 @@ def main():
     def msm_step(bases, scal):
         # C ABI MSM on this rank's chunk (synchronises), then — for N > 1 — NCCL all-gather of the 144-byte partial
         # points and the local sum of N points (algebra_b200/dist.py)
+        if shard == "buckets" and bases.__class__.__module__.startswith("torch"):
+            return D.msm_bucket_sliced(cv, bases, scal)
         return D.msm_sharded(cv, bases, scal)
 
     def timed(fn, steps):
@@ -283,12 +297,12 @@ def main():
     verified = None
     if not args.no_verify:
         r_mod = cv.fr.modulus
-        sc = d_scal.cpu().numpy().view(np.uint64)
-        bb = d_b.cpu().numpy().view(np.uint64)
+        sc = d_scal[c_lo:c_lo + n_chunk].cpu().numpy().view(np.uint64)     # every rank checks one chunk; the totals are gathered
+        bb = d_b[c_lo:c_lo + n_chunk].cpu().numpy().view(np.uint64)
         # scalars are Montgomery residues: value = limbs * R^-1; do the dot product on the raw limbs, fix up at the end
         # 16-bit pieces in float64: products < 2^32, 2^20-term sums < 2^52 -> exact BLAS dot products
         tot, CH = 0, 1 << 20
-        for lo in range(0, n_local, CH):
+        for lo in range(0, n_chunk, CH):
             s16 = sc[lo:lo + CH].view(np.uint16).reshape(-1, 16).astype(np.float64)
             b16 = bb[lo:lo + CH].view(np.uint16).reshape(-1, 4).astype(np.float64)
             m = s16.T @ b16
@@ -327,13 +341,14 @@ def main():
             barrier()
             return max_over_ranks(dt) / steps, r
         e2e_steps = max(1, min(args.steps, 3))
-        h_bases = torch.empty((n_local, 2 * N), dtype=torch.int64).pin_memory()
-        h_scal = torch.empty((n_local, 4), dtype=torch.int64).pin_memory()
-        h_bases.copy_(d_bases)
-        h_scal.copy_(d_scal)
+        h_bases = torch.empty((n_chunk, 2 * N), dtype=torch.int64).pin_memory()
+        h_scal = torch.empty((n_chunk, 4), dtype=torch.int64).pin_memory()
+        h_bases.copy_(d_bases[c_lo:c_lo + n_chunk])
+        h_scal.copy_(d_scal[c_lo:c_lo + n_chunk])
         dt, r2 = timed_host(h_bases.numpy().view(np.uint64), h_scal.numpy().view(np.uint64), e2e_steps)
         e2e = {"value": 1.0 / dt, "unit": "MSM/s", "ms_per_step": dt * 1e3, "steps": e2e_steps, "host_memory": "pinned",
-               "h2d_bytes_per_step": int(n_local * (2 * N * 8 + 32)) * world, "d2h_bytes_per_step": 3 * N * 8 * world,
+               "h2d_bytes_per_step": int(n_chunk * (2 * N * 8 + 32)) * world, "d2h_bytes_per_step": 3 * N * 8 * world,
+               "sharding": "input chunks x%d (host buffers: each GPU receives 1/%d of the bytes)" % (world, world),
                "same_result": bool((ab.into_affine(cv, r2) == ab.into_affine(cv, res)).all())}
         pb, ps = h_bases.numpy().copy(), h_scal.numpy().copy()       # pageable copies
         del h_bases, h_scal
@@ -413,7 +428,8 @@ def main():
             "dtype": "u32 limbs (Montgomery; 12x32-bit Fq, 8x32-bit Fr)", "data": "synthetic",
             "config": {"workload": f"{cv.name} VariableBaseMSM n=2^{args.log_n_msm}, bases b_i*G generated on device, uniform scalars; "
                                    f"NTT leg: Fr radix-2 fft n=2^{args.log_n_ntt}",
-                       "window_c": c, "windows": W, "sharding": f"input chunks x{world}, NCCL all-gather of partial points",
+                       "window_c": c, "windows": W, "sharding": (f"bucket slices x{world} over inputs replicated in every GPU's HBM" if shard == "buckets"
+                                    else f"input chunks x{world}") + ", NCCL all-gather of partial points",
                        "l2": "inputs (>= 2 GiB) larger than L2; no flush needed", "seed": args.seed, "verified_vs_sum_identity": verified},
             "clocks": clocks,
             "phases_ms": phase,

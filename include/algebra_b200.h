@@ -118,6 +118,14 @@ int b200_msm_window_for(int curve, size_t n);
 /* Number of batched-affine pre-reduction levels run between the sort and the XYZZ accumulation (each level halves the
  * bucket runs with affine additions sharing one inversion per batch): 0 = off, -1 = automatic.  Result-neutral. */
 int b200_set_msm_affine_levels(int levels);
+/* Bucket slicing, the second way an MSM shards (the first: input chunks, b200_msm_sw_g1_multi).  After
+ * b200_set_msm_bucket_slice(s, S) the single-device MSM entry points called on this thread accumulate and reduce only the
+ * buckets [nb*s/S, nb*(s+1)/S) of every Pippenger window (window_sums, variable_base/mod.rs:456-487, restricted to a bucket
+ * range), so the S results over the SAME bases and scalars add up (b200_g1_sum) to the complete msm.  Every phase after the
+ * digit extraction shrinks by 1/S, including the per-bucket reduction that input-chunk sharding repeats on every device:
+ * the better split when the inputs are already resident (replicated) on every GPU.  (0, 1) = whole MSM, the default.
+ * The multi-device and resident-bases entry points ignore the setting. */
+int b200_set_msm_bucket_slice(int slice, int slices);
 
 /* sum of k Jacobian points (k x 3N u64, host) -> out_xyz: the local "reduce" after the multi-GPU
  * all-gather of per-rank partial sums (Projective::add_assign, group.rs:450-538). */

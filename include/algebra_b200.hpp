@@ -74,6 +74,18 @@ template <class Curve> struct VariableBaseMSM {
                                    reinterpret_cast<const uint64_t *>(scalars.data()), n, reinterpret_cast<uint64_t *>(&out)));
         return out;
     }
+    // bucket slice `slice` of `slices` of the msm over these (replicated) inputs: the `slices` results add up to msm_unchecked
+    // (b200_set_msm_bucket_slice; one caller per GPU, e.g. one rank per device, then b200_g1_sum over the gathered points)
+    static Projective<Curve> msm_bucket_slice(const std::vector<Affine<Curve>> &bases, const std::vector<Fr> &scalars, int slice, int slices) {
+        check(b200_set_msm_bucket_slice(slice, slices));
+        Projective<Curve> out{};
+        const size_t n = bases.size() < scalars.size() ? bases.size() : scalars.size();
+        const int rc = b200_msm_sw_g1(Curve::ID, reinterpret_cast<const uint64_t *>(bases.data()), reinterpret_cast<const uint64_t *>(scalars.data()), n,
+                                      reinterpret_cast<uint64_t *>(&out));
+        b200_set_msm_bucket_slice(0, 1);
+        check(rc);
+        return out;
+    }
     // VariableBaseMSM::msm_chunks (variable_base/mod.rs:119-150) on the streaming entry points: `step` pairs per push, one reduction
     static Projective<Curve> msm_chunks(const std::vector<Affine<Curve>> &bases, const std::vector<Fr> &scalars, size_t step) {
         if (scalars.size() > bases.size()) throw std::invalid_argument("scalars_stream.len() <= bases_stream.len()");

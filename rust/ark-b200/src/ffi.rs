@@ -20,6 +20,7 @@ extern "C" {
     pub fn b200_msm_sw_g1_dev(curve: c_int, d_bases: *const c_void, d_scalars: *const c_void, n: usize,
                               out_xyz: *mut u64, stream: *mut c_void) -> c_int;
     pub fn b200_device_count() -> c_int;
+    pub fn b200_set_msm_bucket_slice(slice: c_int, slices: c_int) -> c_int;
     pub fn b200_msm_sw_g1_multi(curve: c_int, ngpus: c_int, bases: *const u64, scalars: *const u64, n: usize, out_xyz: *mut u64) -> c_int;
     pub fn b200_bases_upload(curve: c_int, ngpus: c_int, bases: *const u64, n: usize, handle: *mut *mut b200_bases_t) -> c_int;
     pub fn b200_msm_bases(handle: *const b200_bases_t, scalar_kind: c_int, scalars: *const c_void, n: usize, out_xyz: *mut u64) -> c_int;

@@ -239,6 +239,19 @@ impl<C: B200Curve> Drop for ResidentBases<C> {
     }
 }
 
+/// Bucket slice `slice` of `slices` of the MSM over inputs that every caller holds in full (an SRS replicated on every GPU,
+/// one process or thread per device): the `slices` results add up to `msm_b200`.  `b200_set_msm_bucket_slice` + the
+/// streaming entry points, which run on the calling thread's current device.
+pub fn msm_bucket_slice_b200<C: B200Curve>(bases: &[Affine<C>], scalars: &[C::ScalarField], slice: usize, slices: usize) -> Result<Projective<C>, usize> {
+    if bases.len() != scalars.len() {
+        return Err(bases.len().min(scalars.len()));
+    }
+    ffi::check(unsafe { ffi::b200_set_msm_bucket_slice(slice as i32, slices as i32) });
+    let out = msm_chunks_b200::<C>(bases, scalars, bases.len().max(1));
+    ffi::check(unsafe { ffi::b200_set_msm_bucket_slice(0, 1) });
+    Ok(out)
+}
+
 /// `VariableBaseMSM::msm_chunks` (variable_base/mod.rs:119-150) on the streaming entry points: every chunk of `step` pairs is
 /// pushed (H2D under the previous chunk's arithmetic), one bucket reduction at the end.
 pub fn msm_chunks_b200<C: B200Curve>(bases: &[Affine<C>], scalars: &[C::ScalarField], step: usize) -> Projective<C> {

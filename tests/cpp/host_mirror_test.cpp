@@ -52,6 +52,12 @@ int main(int argc, char **argv) {
             printf("gpu_msm_single %d\n", (int)same(aff(VariableBaseMSM<C>::msm_unchecked(B, S)), want));
             printf("gpu_msm_multi %d\n", (int)same(aff(VariableBaseMSM<C>::msm_unchecked_multi(B, S, devices)), want));
             printf("gpu_msm_chunks %d\n", (int)same(aff(VariableBaseMSM<C>::msm_chunks(B, S, 1200)), want));
+            {   // three bucket slices over the same inputs, summed with b200_g1_sum
+                Projective<C> parts[3], sum{};
+                for (int i = 0; i < 3; i++) parts[i] = VariableBaseMSM<C>::msm_bucket_slice(B, S, i, 3);
+                const int rc = b200_g1_sum(C::ID, reinterpret_cast<const uint64_t *>(parts), 3, reinterpret_cast<uint64_t *>(&sum));
+                printf("gpu_msm_slices %d\n", (int)(rc == 0 && same(aff(sum), want)));
+            }
             ResidentBases<C> srs(B, devices);
             printf("gpu_msm_resident %d\n", (int)same(aff(std::get<0>(srs.msm(S))), want));
             S.pop_back();

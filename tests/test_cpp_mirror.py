@@ -43,5 +43,5 @@ def test_cpp_mirror_on_gpu(binary):
     assert kv["gpu_msm_identity"] == "1" and kv["gpu_ntt_roundtrip"] == "1"
     # single-device, all-devices (b200_msm_sw_g1_multi), streaming and resident-bases entry points agree with (sum i) * G
     assert int(kv["gpu_devices"]) >= 1
-    for k in ("gpu_msm_single", "gpu_msm_multi", "gpu_msm_chunks", "gpu_msm_resident", "gpu_resident_mismatch"):
+    for k in ("gpu_msm_single", "gpu_msm_multi", "gpu_msm_chunks", "gpu_msm_slices", "gpu_msm_resident", "gpu_resident_mismatch"):
         assert kv[k] == "1", k

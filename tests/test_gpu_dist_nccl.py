@@ -97,6 +97,12 @@ def test_multi_device_c_abi(ngpus):
     want = _expected(0, d_b.cpu().numpy().view(np.uint64), sh)
     got = ab.into_affine(0, VB.msm_multi(0, bh, sh, ngpus))
     assert (got == want).all()
+    VB.set_bucket_slice(1, 2)      # input-chunk sharding computes whole MSMs: a bucket slice set on the thread is ignored ...
+    try:
+        assert (ab.into_affine(0, VB.msm_multi(0, bh, sh, ngpus)) == want).all()
+        assert not (ab.into_affine(0, ab.msm(0, bh, sh)) == want).all()   # ... and still in force afterwards for the single-device call
+    finally:
+        VB.set_bucket_slice(0, 1)
     # resident bases: upload once (sharded over the devices), reuse for two scalar vectors
     h = VB.bases_upload(0, bh, ngpus)
     try:
@@ -108,3 +114,45 @@ def test_multi_device_c_abi(ngpus):
         assert (ab.into_affine(0, VB.msm_with_bases(h, sh[:1000])) == _expected(0, d_b.cpu().numpy().view(np.uint64)[:1000], sh[:1000])).all()
     finally:
         VB.bases_free(h)
+
+
+def _worker_slices(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import algebra_b200 as ab
+    from algebra_b200 import _lib
+    from algebra_b200 import dist as D
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    d_bases = torch.empty((n, 12), dtype=torch.int64, device="cuda")
+    d_b = torch.empty((n,), dtype=torch.int64, device="cuda")
+    d_s = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+    _lib.check(L.b200_gen_bases_dev(0, 4811, n, d_bases.data_ptr(), d_b.data_ptr(), st))    # replicated inputs: same seed on every rank
+    _lib.check(L.b200_gen_scalars_dev(0, 4812, n, d_s.data_ptr(), st))
+    xyz = D.msm_bucket_sliced(0, d_bases, d_s)
+    got = ab.into_affine(0, xyz)
+    want = _expected(0, d_b.cpu().numpy().view(np.uint64), d_s.cpu().numpy().view(np.uint64))
+    q.put((rank, bool((got == want).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1 << 14, 4097])
+def test_bucket_sliced_msm_nccl_world2(n):
+    """bucket-slice sharding over NCCL: every rank holds all pairs and reduces its own range of every window's buckets"""
+    if _ngpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_slices, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

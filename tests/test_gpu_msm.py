@@ -381,3 +381,57 @@ def test_chunked_device_path(monkeypatch):
         assert (ab.into_affine(cid, ab.msm(cid, d_bases, d_s)) == want).all()
     monkeypatch.delenv("B200_MSM_FORCE_CHUNKS")
     assert (ab.into_affine(cid, ab.msm(cid, d_bases, d_s)) == want).all()
+
+
+@pytest.mark.parametrize("cid,n,c,slices", [(0, 1 << 12, 0, 2), (0, 1 << 12, 9, 3), (0, 3001, 12, 8), (1, 1 << 12, 10, 4), (0, 1 << 12, 2, 5),
+                                            (0, 1 << 12, 1, 2), (0, 1 << 16, 0, 8), (0, 1 << 12, 13, 64)])
+def test_bucket_slices_add_up(cid, n, c, slices):
+    """b200_set_msm_bucket_slice: the S partial results over the same inputs (each restricted to a contiguous range of every
+    window's buckets) sum to the complete msm, for windows with fewer buckets than slices too (c = 1, 2: slice 0 takes them
+    whole, the others return the identity), with and without affine levels, host and device inputs."""
+    d_bases, d_b, d_s = synth(cid, n, 1234 + slices)
+    want = expected_from_b(cid, from_dev(d_b), from_dev(d_s))
+    bh, sh = from_dev(d_bases), from_dev(d_s)
+    try:
+        M.set_window(c)
+        for levels in (-1, 2):
+            M.set_affine_levels(levels)
+            parts = []
+            for i in range(slices):
+                M.set_bucket_slice(i, slices)
+                parts.append(ab.msm(cid, d_bases, d_s) if i % 2 == 0 else ab.msm(cid, bh, sh))
+            M.set_bucket_slice(0, 1)
+            assert (ab.into_affine(cid, M.sum_points(cid, np.stack(parts))) == want).all(), levels
+            # a slice is a proper part of the sum (not the whole MSM repeated)
+            if c == 0 or c > 3:
+                assert not (ab.into_affine(cid, parts[0]) == want).all()
+    finally:
+        M.set_bucket_slice(0, 1)
+        M.set_affine_levels(-1)
+        M.set_window(0)
+    with pytest.raises(_lib.B200Error):
+        M.set_bucket_slice(2, 2)
+    with pytest.raises(_lib.B200Error):
+        M.set_bucket_slice(0, 0)
+
+
+def test_bucket_slices_small_scalars_streams_and_chunks(monkeypatch):
+    """slices with a single-window geometry (u8 scalars), through the streaming entry points, and on the chunked device path"""
+    cid, n = 0, 5000
+    d_bases, d_b, d_s = synth(cid, n, 77)
+    bh, sh = from_dev(d_bases), from_dev(d_s)
+    rnd = np.random.default_rng(5)
+    small = rnd.integers(0, 256, n, dtype=np.uint8)
+    full_small = ab.into_affine(cid, ab.msm_u8(cid, bh, small))
+    full = ab.into_affine(cid, ab.msm(cid, bh, sh))
+    try:
+        parts, parts_stream = [], []
+        for i in range(3):
+            M.set_bucket_slice(i, 3)
+            parts.append(ab.msm_u8(cid, bh, small))
+            parts_stream.append(ab.msm_chunks(cid, bh, sh, step=1024))
+        M.set_bucket_slice(0, 1)
+        assert (ab.into_affine(cid, M.sum_points(cid, np.stack(parts))) == full_small).all()
+        assert (ab.into_affine(cid, M.sum_points(cid, np.stack(parts_stream))) == full).all()
+    finally:
+        M.set_bucket_slice(0, 1)

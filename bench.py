@@ -410,13 +410,16 @@ def main():
 
     if rank == 0:
         c, W = tm["c"], tm["windows"]
-        modmuls, wide, byts = msm_work(n_local, c, W, 2 * N)
+        # per-rank work: n/N points x W windows either way; a bucket slice also reduces only 1/N of the buckets
+        modmuls, wide, byts = msm_work(n_chunk, c, W, 2 * N)
+        bshare = (1.0 / world) if shard == "buckets" else 1.0
+        wide -= (1.0 - bshare) * 14.0 * (1 << c) * W * (2 * (2 * N) ** 2 + 2 * N)
         acc_s = phase["accumulate"] * 1e-3
-        acc_wide = 10.0 * n_local * W * (2 * (2 * N) ** 2 + 2 * N)
+        acc_wide = 10.0 * n_chunk * W * (2 * (2 * N) ** 2 + 2 * N)
         # multiplications actually executed: 4 affine levels leave 1/16 of the entries to the XYZZ kernel (10 each), the levels cost
         # 6 + 570/batch (~6.6) per addition; bucket reduction ~28 per bucket; BN254 runs without levels
         lv = 4 if N == 6 else 0
-        executed_modmuls = n_local * W * ((1 - 0.5 ** lv) * 6.6 + 0.5 ** lv * 10.0) + 28.0 * (1 << (c - 1)) * W
+        executed_modmuls = n_chunk * W * ((1 - 0.5 ** lv) * 6.6 + 0.5 ** lv * 10.0) + 28.0 * (1 << (c - 1)) * W * bshare
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tp) and world == 1 and args.log_n_msm == 26 and args.curve == 0:
